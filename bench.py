@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched small-matrix hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload sym_solve3|sym_solve6|sym_invert6|sym_solve10|dense_inv4_f64|...]
+
+Metric (BASELINE.json): batched sym-solve matrices/s and achieved HBM GB/s
+vs peak.  A "step" is one pass of the hot path over the whole workload:
+the default workload is BASELINE.json configs[1], the 256^3-voxel 3x3
+compact-symmetric solve in fp32 (16 777 216 matrices, 48 B each).
+
+  value   whole-job matrices/s with operands resident in HBM, CUDA events on
+          the launch stream, K back-to-back launches through the C ABI.
+  e2e     the same metric through the public API with HOST (pinned) operands:
+          chunked H2D -> kernel -> D2H inside the timed region.
+  N > 1   strong scaling (north star): the batch is split into N contiguous
+          slabs, one process per GPU, no data-path collective; torch.distributed
+          is used only for the barrier and the max-over-ranks of the time.
+
+One JSON line on stdout (rank 0).  With --impl reference the reference's CPU
+algorithm (oracle/ref_port.py, kind "port") is timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L2_BYTES = 126 << 20
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+# name -> (kind, n, dtype, voxels-per-side or batch, description)
+WORKLOADS = {
+    "sym_solve3": dict(kind="sym_solve", n=3, dtype="f32", batch=256 ** 3,
+                       desc="256^3-voxel 3x3 compact-sym solve fp32 (BASELINE.json configs[1])"),
+    "sym_solve6": dict(kind="sym_solve", n=6, dtype="f32", batch=192 ** 3,
+                       desc="192^3-voxel 6x6 compact-sym solve fp32 (configs[2])"),
+    "sym_invert6": dict(kind="sym_invert", n=6, dtype="f32", batch=192 ** 3,
+                        desc="192^3-voxel 6x6 compact-sym invert fp32 (configs[2])"),
+    "sym_solve10": dict(kind="sym_solve", n=10, dtype="f32", batch=160 ** 3,
+                        desc="160^3-voxel 10x10 compact-sym solve fp32 (configs[4])"),
+    "sym_matvec3": dict(kind="sym_matvec", n=3, dtype="f32", batch=256 ** 3,
+                        desc="256^3-voxel 3x3 compact-sym matvec fp32"),
+    "sym_solve3_1m": dict(kind="sym_solve", n=3, dtype="f32", batch=1_000_000,
+                          desc="1M 3x3 compact-sym solve fp32 (configs[0])"),
+    "dense_inv4_f64": dict(kind="batch_inv", n=4, dtype="f64", batch=64 << 20,
+                           desc="64M general 4x4 inverse fp64 (configs[3])"),
+    "dense_det4_f64": dict(kind="batch_det", n=4, dtype="f64", batch=64 << 20,
+                           desc="64M general 4x4 det fp64 (configs[3])"),
+    "dense_solve4_f64": dict(kind="batch_solve", n=4, dtype="f64", batch=64 << 20,
+                             desc="64M general 4x4 LU solve fp64 (configs[3])"),
+}
+
+
+def record_lengths(kind: str, n: int):
+    """(input record lengths, output record length) in elements."""
+    nn = n * (n + 1) // 2
+    return {
+        "sym_solve": ([nn, n], n),
+        "sym_matvec": ([nn, n], n),
+        "sym_invert": ([nn], nn),
+        "batch_inv": ([n * n], n * n),
+        "batch_det": ([n * n], 1),
+        "batch_solve": ([n * n, n], n),
+    }[kind]
+
+
+def algorithmic_bytes(kind: str, n: int, esize: int) -> int:
+    """Minimum HBM traffic per matrix."""
+    ins, out = record_lengths(kind, n)
+    return (sum(ins) + out) * esize
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload: str):
+    """dram__bytes_read+write per launch from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------
+# synthetic data, generated on the device (seeded), shaped like the workload
+# --------------------------------------------------------------------------
+
+def make_inputs(kind: str, n: int, dtype: torch.dtype, batch: int, device, seed: int):
+    g = torch.Generator(device=device).manual_seed(seed)
+    if kind.startswith("sym"):
+        out = []
+        chunk = 1 << 21
+        for b0 in range(0, batch, chunk):
+            b = min(chunk, batch - b0)
+            a = torch.randn(b, n, n, device=device, dtype=dtype, generator=g)
+            full = a @ a.transpose(-1, -2)
+            full.diagonal(0, -1, -2).add_(n)
+            iu = torch.triu_indices(n, n, 1, device=device)
+            out.append(torch.cat([full.diagonal(0, -1, -2), full[..., iu[0], iu[1]]], -1))
+        mat = torch.cat(out).contiguous()
+        if kind == "sym_invert":
+            return [mat]
+        return [mat, torch.randn(batch, n, device=device, dtype=dtype, generator=g)]
+    a = torch.randn(batch, n, n, device=device, dtype=dtype, generator=g)
+    a.diagonal(0, -1, -2).add_(10)
+    if kind == "batch_solve":
+        return [a, torch.randn(batch, n, device=device, dtype=dtype, generator=g)]
+    return [a]
+
+
+def abi_call(lib, kind: str, n: int, code: int, batch: int, ins, out, stream: int):
+    """One pass of the hot path through the C ABI (include/nfm.h)."""
+    lens, olen = record_lengths(kind, n)
+    p = [t.data_ptr() for t in ins]
+    if kind == "sym_solve":
+        return lib.nfm_sym_solve(code, n, 2, 0, batch, p[0], lens[0], p[1], lens[1], None, 0, out.data_ptr(), olen, stream)
+    if kind == "sym_matvec":
+        return lib.nfm_sym_matvec(code, n, 2, batch, p[0], lens[0], p[1], lens[1], None, 0, 0, out.data_ptr(), olen, stream)
+    if kind == "sym_invert":
+        return lib.nfm_sym_invert(code, n, 0, 0, batch, p[0], lens[0], out.data_ptr(), olen, stream)
+    if kind == "batch_inv":
+        return lib.nfm_batch_inv(code, n, 0, 1, batch, p[0], lens[0], out.data_ptr(), olen, stream)
+    if kind == "batch_det":
+        return lib.nfm_batch_det(code, n, batch, p[0], lens[0], out.data_ptr(), olen, stream)
+    if kind == "batch_solve":
+        return lib.nfm_batch_solve(code, n, 1, 2, batch, p[0], lens[0], p[1], lens[1], out.data_ptr(), olen, stream)
+    raise ValueError(kind)
+
+
+def api_call(kind: str, ins, out):
+    """The call a user makes (public drop-in API)."""
+    from nitorch_fastmath_b200 import batched, sugar, sym
+    if kind == "sym_solve":
+        return sym.sym_solve(ins[0], ins[1], out=out)
+    if kind == "sym_matvec":
+        return sym.sym_matvec(ins[0], ins[1], out=out)
+    if kind == "sym_invert":
+        return sym.sym_invert(ins[0], out=out)
+    if kind == "batch_inv":
+        return batched.batchinv(ins[0])
+    if kind == "batch_det":
+        return batched.batchdet(ins[0])
+    if kind == "batch_solve":
+        return sugar.solvevec(ins[0], ins[1])
+    raise ValueError(kind)
+
+
+def oracle_call(kind: str, ins):
+    from oracle import ref_port as P
+    if kind == "sym_solve":
+        return P.sym_solve(ins[0], ins[1])
+    if kind == "sym_matvec":
+        return P.sym_matvec(ins[0], ins[1])
+    if kind == "sym_invert":
+        return P.sym_invert(ins[0])
+    if kind == "batch_inv":
+        return P.batchinv(ins[0])
+    if kind == "batch_det":
+        return P.batchdet(ins[0])
+    if kind == "batch_solve":
+        return P.solvevec(ins[0], ins[1])
+    raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------
+# clocks during the timed region (NVML)
+# --------------------------------------------------------------------------
+
+class ClockSampler:
+    REASONS = {
+        0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+        0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int, period: float = 0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._period = period
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------
+
+def cpu_baseline(kind, n, dtype, batch, steps=3, warmup=1, budget_s=20.0):
+    """The reference's CPU algorithm (oracle port, torch CPU ops exactly as the
+    reference issues them) on all host cores, on a bounded sample of the
+    workload: the sample is sized from a calibration run so that
+    (warmup + steps) passes take about ``budget_s`` seconds."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen_dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    cal = min(batch, 1 << 20)
+    ins = [t.cpu() for t in make_inputs(kind, n, dtype, cal, gen_dev, seed=0)]
+    oracle_call(kind, [t[:4096] for t in ins])            # TorchScript-free, but warms the allocator
+    t0 = time.perf_counter()
+    oracle_call(kind, ins)
+    per_matrix = (time.perf_counter() - t0) / cal
+    sample = int(budget_s / (steps + warmup) / per_matrix)
+    sample = max(min(sample, batch), min(batch, 1 << 16))
+    if sample != cal:
+        ins = [t.cpu() for t in make_inputs(kind, n, dtype, sample, gen_dev, seed=0)]
+    for _ in range(warmup):
+        oracle_call(kind, ins)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle_call(kind, ins)
+        times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": sample / mean, "unit": "matrices/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} of {batch} matrices per step, {steps} steps after {warmup} warm-up; "
+                      "oracle/ref_port.py = the reference's torch-CPU algorithm",
+            "best_value": sample / min(times), "seconds_per_step": mean, "sample_matrices": sample}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sym_solve3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override the workload's batch (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world != 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    w = WORKLOADS[args.workload]
+    kind, n = w["kind"], w["n"]
+    dtype = torch.float32 if w["dtype"] == "f32" else torch.float64
+    esize = 4 if dtype == torch.float32 else 8
+    batch = args.batch or w["batch"]
+    alg = algorithmic_bytes(kind, n, esize)
+    config = {"workload": w["desc"], "routine": kind, "n": n, "batch": batch, "bytes_per_matrix": alg}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base = cpu_baseline(kind, n, dtype, batch, steps=args.steps, warmup=args.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": "batched sym-solve matrices/sec" if kind == "sym_solve" else f"{kind} matrices/sec",
+                "value": base["value"], "unit": "matrices/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": base["seconds_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": w["dtype"],
+                "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in the product)")
+    from nitorch_fastmath_b200 import _lib
+    from nitorch_fastmath_b200.shard import shard_bounds
+    lib = _lib.load()
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    begin, end = shard_bounds(batch, world, rank)
+    my = end - begin
+    code = 0 if dtype == torch.float32 else 1
+    lens, olen = record_lengths(kind, n)
+
+    # operand sets: rotate enough distinct sets that consecutive steps never
+    # find their data in L2 (or one set if it is already several times L2)
+    set_bytes = my * alg
+    nsets = 1 if set_bytes >= 3 * L2_BYTES else min(8, math.ceil(3 * L2_BYTES / max(set_bytes, 1)))
+    sets = []
+    for s in range(nsets):
+        ins = make_inputs(kind, n, dtype, my, dev, seed=1000 * rank + s)
+        out = torch.empty(my, olen, device=dev, dtype=dtype) if olen > 1 else torch.empty(my, device=dev, dtype=dtype)
+        sets.append((ins, out))
+    config["l2"] = (f"per-GPU working set {set_bytes / 2**20:.0f} MiB > L2" if nsets == 1 else
+                    f"rotating {nsets} operand sets of {set_bytes / 2**20:.0f} MiB (> 3x L2 in total)")
+
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step(i):
+        ins, out = sets[i % nsets]
+        rc = abi_call(lib, kind, n, code, my, ins, out, stream)
+        if rc:
+            _lib.check(rc, "bench step")
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        sync()
+    launches = _lib.launch_count() - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = batch / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel: algorithmic bytes per launch / average launch duration
+    peak, peak_src = measured_peak()
+    local_ms = ev0.elapsed_time(ev1) / args.steps
+    achieved = my * alg / (local_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "kernel": "tile_kernel<%s n=%d %s> (1 launch/step/GPU)" % (kind, n, w["dtype"]),
+                "bytes_per_launch": my * alg, "avg_launch_us": local_ms * 1e3}
+
+    # end to end: host (pinned) operands through the public API
+    e2e = None
+    if not args.no_e2e and kind.startswith("sym"):
+        ins0, _ = sets[0]
+        host_in = [t.cpu().pin_memory() for t in ins0]
+        host_out = torch.empty((my, olen), dtype=dtype).pin_memory()
+        ksteps = args.e2e_steps or max(3, min(args.steps, 10))
+        for _ in range(2):
+            api_call(kind, host_in, host_out)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            api_call(kind, host_in, host_out)   # synchronises its pipeline streams before returning
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": batch / (dt / ksteps), "unit": "matrices/s",
+               "h2d_bytes_per_step": sum(t.numel() * esize for t in host_in) * world,
+               "d2h_bytes_per_step": host_out.numel() * esize * world, "steps": ksteps,
+               "ms_per_step": dt / ksteps * 1e3,
+               "api": "nitorch_fastmath_b200.sym.%s(pinned CPU tensors, out=pinned CPU tensor)" % kind}
+
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        base = cpu_baseline(kind, n, dtype, batch, steps=3, warmup=1, budget_s=20.0)
+
+    if rank == 0:
+        line = {"metric": "batched sym-solve matrices/sec" if kind == "sym_solve" else f"{kind} matrices/sec",
+                "value": value, "unit": "matrices/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": w["dtype"], "data": "synthetic", "config": config, "roofline": roofline,
+                "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e}
+        if base is not None:
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

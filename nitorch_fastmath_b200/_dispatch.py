@@ -1,0 +1,155 @@
+"""Host-side plumbing between torch tensors and the C ABI.
+
+torch is used for allocation, broadcasting metadata and the current stream
+only.  Every operand is handed to the library as (device pointer, batch
+stride in elements): its record dims (the last ``rec_ndim`` dims) must be
+contiguous and its batch dims must collapse to one stride -- 0 for a fully
+broadcast operand, ``record length`` for a dense one, anything else takes the
+library's strided kernel.  Operands that do not collapse are materialised
+with ``.contiguous()`` (one extra pass; documented in DESIGN.md).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPE_CODE = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dtype]
+    except KeyError:
+        raise TypeError(f"nitorch_fastmath_b200 supports float32 and float64, got {dtype}") from None
+
+
+def compute_dtype(*tensors, dtype: Optional[torch.dtype] = None) -> torch.dtype:
+    if dtype is None:
+        dtype = tensors[0].dtype
+        for t in tensors[1:]:
+            dtype = torch.promote_types(dtype, t.dtype)
+    if dtype not in _DTYPE_CODE:
+        if dtype.is_floating_point:      # half / bfloat16 inputs compute in float32
+            dtype = torch.float32
+        else:
+            raise TypeError(f"unsupported dtype {dtype}")
+    return dtype
+
+
+def common_device(*tensors) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors[1:]:
+        if t.device != dev:
+            raise RuntimeError(f"operands live on different devices: {dev} and {t.device}")
+    return dev
+
+
+def require_cuda(dev: torch.device) -> None:
+    if dev.type != "cuda":
+        raise RuntimeError("internal: device path called with non-CUDA tensors")
+
+
+def _record_contiguous(t: torch.Tensor, rec_ndim: int) -> bool:
+    expect = 1
+    for d in range(t.dim() - 1, t.dim() - 1 - rec_ndim, -1):
+        if t.shape[d] != 1 and t.stride(d) != expect:
+            return False
+        expect *= t.shape[d]
+    return True
+
+
+def _collapse(shape: Sequence[int], strides: Sequence[int]) -> Optional[int]:
+    """Single stride that walks ``shape`` in row-major order, or None."""
+    dims = [(n, s) for n, s in zip(shape, strides) if n != 1]
+    if not dims:
+        return None  # single element: any stride works
+    for (n0, s0), (n1, s1) in zip(dims[:-1], dims[1:]):
+        if s0 != s1 * n1:
+            return -1
+    return dims[-1][1]
+
+
+class Operand:
+    """(pointer, batch stride) view of a tensor; keeps the storage alive."""
+    __slots__ = ("tensor", "ptr", "stride")
+
+    def __init__(self, tensor: torch.Tensor, stride: int):
+        self.tensor = tensor
+        self.ptr = tensor.data_ptr()
+        self.stride = stride
+
+
+def as_operand(t: torch.Tensor, batch_shape: Tuple[int, ...], rec_ndim: int, dtype: torch.dtype) -> Operand:
+    """Broadcast ``t``'s batch dims to ``batch_shape`` and express it as one stride."""
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    rec_shape = tuple(t.shape[t.dim() - rec_ndim:]) if rec_ndim else ()
+    rec_len = math.prod(rec_shape)
+    if not _record_contiguous(t, rec_ndim):
+        t = t.contiguous()
+    full = t.expand(*batch_shape, *rec_shape)
+    nb = len(batch_shape)
+    stride = _collapse(full.shape[:nb], full.stride()[:nb])
+    if stride is None:
+        stride = rec_len
+    elif stride < 0:
+        full = full.contiguous()
+        stride = rec_len
+    return Operand(full, stride)
+
+
+def out_operand(out: Optional[torch.Tensor], shape: Tuple[int, ...], rec_ndim: int, dtype: torch.dtype,
+                device: torch.device):
+    """Returns (operand to write into, tensor to return, needs_copy_back)."""
+    if out is None:
+        res = torch.empty(shape, dtype=dtype, device=device)
+        rec_len = math.prod(shape[len(shape) - rec_ndim:]) if rec_ndim else 1
+        return Operand(res, rec_len), res, False
+    if tuple(out.shape) != tuple(shape):
+        raise RuntimeError(f"out has shape {tuple(out.shape)}, expected {tuple(shape)}")
+    if out.device != device:
+        raise RuntimeError("out lives on a different device")
+    nb = len(shape) - rec_ndim
+    ok = out.dtype == dtype and _record_contiguous(out, rec_ndim)
+    stride = _collapse(out.shape[:nb], out.stride()[:nb]) if ok else -1
+    rec_len = math.prod(shape[nb:]) if rec_ndim else 1
+    if stride is None:
+        stride = rec_len
+    if not ok or stride < 0 or (stride == 0 and math.prod(shape[:nb]) > 1):
+        tmp = torch.empty(shape, dtype=dtype, device=device)
+        return Operand(tmp, rec_len), out, True
+    return Operand(out, stride), out, False
+
+
+def batch_count(batch_shape: Sequence[int]) -> int:
+    return math.prod(batch_shape)
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def packed_order(length: int) -> int:
+    """N from N(N+1)/2 (reference: _impl/sym.py:37)."""
+    n = int((math.sqrt(1 + 8 * length) - 1) // 2)
+    if n * (n + 1) // 2 != length:
+        raise ValueError(f"{length} is not a packed-symmetric length N(N+1)/2")
+    return n
+
+
+def detect_layout(nn: int, n: int) -> int:
+    """Compact layout from the two trailing sizes (reference sym.py:16-24)."""
+    if nn == n * (n + 1) // 2:
+        return _lib.LAYOUT_SYM      # also covers n == 1 where all four coincide
+    if nn == 1:
+        return _lib.LAYOUT_SCALED_IDENTITY
+    if nn == n:
+        return _lib.LAYOUT_DIAG
+    if nn == n * n:
+        return _lib.LAYOUT_FULL
+    raise ValueError(f"matrix with {nn} coefficients does not match a vector of length {n}: "
+                     f"expected 1, {n}, {n * (n + 1) // 2} or {n * n}")

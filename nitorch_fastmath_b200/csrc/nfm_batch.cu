@@ -1,0 +1,50 @@
+// dense batched inverse / det / matvec / solve for one scalar type
+// (-DNFM_SCALAR) and one part (-DNFM_PART)
+#include "nfm_dense_ops.cuh"
+#include "nfm_impl.cuh"
+#include "nfm_sym_ops.cuh"
+
+namespace nfm {
+
+template <typename T, int ALGO> struct InvBind { template <int N> using Op = BatchInvOp<T, N, ALGO>; };
+template <typename T> struct DetBind { template <int N> using Op = BatchDetOp<T, N>; };
+template <typename T> struct MvBind { template <int N> using Op = BatchMatvecOp<T, N>; };
+template <typename T, int ALGO> struct SolBind { template <int N> using Op = BatchSolveOp<T, N, ALGO>; };
+
+#if NFM_PART == 0
+template <typename T>
+int batch_inv_lu_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<InvBind<T, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+}
+template int batch_inv_lu_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+#elif NFM_PART == 1
+template <typename T>
+int batch_inv_ldl_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<InvBind<T, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+}
+template <typename T>
+int batch_det_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<DetBind<T>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+}
+template <typename T>
+int batch_matvec_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<MvBind<T>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+}
+template int batch_inv_ldl_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+template int batch_det_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+template int batch_matvec_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+#elif NFM_PART == 2
+template <typename T>
+int batch_solve_lu_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<SolBind<T, NFM_ALGO_LU>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+}
+template int batch_solve_lu_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+#else
+template <typename T>
+int batch_solve_ldl_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<SolBind<T, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+}
+template int batch_solve_ldl_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+#endif
+
+}  // namespace nfm

@@ -1,0 +1,181 @@
+// nfm_common.cuh -- shared device helpers: sm_100a PTX wrappers (mbarrier, 1-D
+// TMA bulk copies), record <-> register movers, launch parameter block.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nfm.h"
+
+namespace nfm {
+
+using i64 = long long;
+
+// One batched operand: base pointer + batch stride in elements (0 = broadcast).
+struct Operand {
+  const void* ptr;
+  i64 stride;
+};
+
+constexpr int kMaxIn = 3;
+
+// Launch parameter block shared by every op.
+struct KParams {
+  Operand in[kMaxIn];
+  void* out;
+  i64 out_stride;
+  i64 batch;     // matrices handled by this launch
+  int present;   // bit i set: input operand i is present
+  int flags;     // op-specific
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+// make mbarrier.init visible to the async proxy (TMA unit)
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NFM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NFM_DONE;\n"
+      "bra NFM_WAIT;\n"
+      "NFM_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// L2 eviction policy for streamed-once data
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// 1-D TMA: global -> shared, completion counted in bytes on an mbarrier.
+// src, dst 16-byte aligned, bytes % 16 == 0.   SASS: UBLKCP
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// 1-D TMA: shared -> global, tracked by the bulk async-group of the issuing thread.
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+
+template <int kPending>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+// generic-proxy smem writes -> visible to the async proxy (before a bulk store)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
+// record movers: a record is L contiguous elements of T.  Within a staged tile
+// record r starts at r*L*sizeof(T) from a 16-byte aligned base, so its
+// alignment is gcd(L*sizeof(T), 16); use the widest access that allows.
+// (Widest access also decides shared-memory bank behaviour: a stride that is
+// an odd multiple of the access width is conflict free.)
+// ---------------------------------------------------------------------------
+template <typename T, int L>
+struct RecAccess {
+  static constexpr int kBytes = L * int(sizeof(T));
+  static constexpr int kVecBytes = (kBytes % 16 == 0) ? 16 : (kBytes % 8 == 0) ? 8 : (kBytes % 4 == 0) ? 4 : int(sizeof(T));
+  static constexpr int kVec = kVecBytes / int(sizeof(T));  // elements per access
+  static_assert(kVec >= 1, "record narrower than one element");
+};
+
+template <int kBytes>
+struct VecType;
+template <>
+struct VecType<4> { using type = uint32_t; };
+template <>
+struct VecType<8> { using type = uint2; };
+template <>
+struct VecType<16> { using type = uint4; };
+
+template <typename T, int L>
+__device__ __forceinline__ void load_record(const T* __restrict__ src, T (&r)[L]) {
+  using A = RecAccess<T, L>;
+  using V = typename VecType<A::kVecBytes>::type;
+  constexpr int kChunks = L / A::kVec;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    V v = reinterpret_cast<const V*>(src)[c];
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int k = 0; k < A::kVec; ++k) r[c * A::kVec + k] = e[k];
+  }
+}
+
+template <typename T, int L>
+__device__ __forceinline__ void store_record(T* __restrict__ dst, const T (&r)[L]) {
+  using A = RecAccess<T, L>;
+  using V = typename VecType<A::kVecBytes>::type;
+  constexpr int kChunks = L / A::kVec;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    V v;
+    T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int k = 0; k < A::kVec; ++k) e[k] = r[c * A::kVec + k];
+    reinterpret_cast<V*>(dst)[c] = v;
+  }
+}
+
+// element-wise movers for the strided kernel (no alignment assumption)
+template <typename T, int L>
+__device__ __forceinline__ void load_record_scalar(const T* src, T (&r)[L]) {
+#pragma unroll
+  for (int k = 0; k < L; ++k) r[k] = src[k];  // plain loads: src may alias the output (in-place ops)
+}
+
+template <typename T, int L>
+__device__ __forceinline__ void store_record_scalar(T* dst, const T (&r)[L]) {
+#pragma unroll
+  for (int k = 0; k < L; ++k) dst[k] = r[k];
+}
+
+template <typename T, int L>
+__device__ __forceinline__ void zero_record(T (&r)[L]) {
+#pragma unroll
+  for (int k = 0; k < L; ++k) r[k] = T(0);
+}
+
+}  // namespace nfm

@@ -1,0 +1,135 @@
+// nfm_dense_math.cuh -- per-matrix register math for dense row-major n x n
+// matrices: matvec, closed-form det / inverse for n <= 3 (the reference's
+// TorchScript closed forms, _impl/batched.py:22-32, :67-98), in-place
+// Gauss-Jordan inverse with partial pivoting above.
+#pragma once
+
+#include "nfm_common.cuh"
+#include "nfm_sym_math.cuh"
+
+namespace nfm {
+
+template <typename T, int M, int N>
+__device__ __forceinline__ void dense_matvec_reg(const T (&a)[M * N], const T (&v)[N], T (&y)[M]) {
+  // left-to-right accumulation, as matvec1/2/3 (_impl/batched.py:134-151)
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    T s = a[i * N] * v[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) s += a[i * N + j] * v[j];
+    y[i] = s;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T dense_det2(const T* a) { return a[0] * a[3] - a[1] * a[2]; }
+
+template <typename T>
+__device__ __forceinline__ T dense_det3(const T* a) {
+  // _impl/batched.py:27-32
+  return a[0] * (a[4] * a[8] - a[5] * a[7]) + a[1] * (a[5] * a[6] - a[3] * a[8]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+}
+
+// max|a| - min|a| over the entries: the reference's determinant regulariser
+// scale (_impl/batched.py:74-76, :94-96)
+template <typename T, int L>
+__device__ __forceinline__ T abs_range(const T (&a)[L]) {
+  T hi = tabs(a[0]), lo = hi;
+#pragma unroll
+  for (int k = 1; k < L; ++k) {
+    const T c = tabs(a[k]);
+    hi = c > hi ? c : hi;
+    lo = c < lo ? c : lo;
+  }
+  return hi - lo;
+}
+
+// closed-form inverse n = 1..3; `regularise` adds range * 1e-12 to the determinant
+template <typename T, int N>
+__device__ __forceinline__ void dense_inv_closed(const T (&a)[N * N], bool regularise, T (&f)[N * N]) {
+  static_assert(N >= 1 && N <= 3, "closed forms cover n = 1..3");
+  if constexpr (N == 1) {
+    f[0] = T(1) / a[0];  // reciprocal, _impl/batched.py:128
+  } else if constexpr (N == 2) {
+    T dt = dense_det2(a);
+    if (regularise) dt += abs_range(a) * T(1e-12);
+    f[0] = a[3] / dt;
+    f[1] = -a[1] / dt;
+    f[2] = -a[2] / dt;
+    f[3] = a[0] / dt;
+  } else {
+    T dt = dense_det3(a);
+    if (regularise) dt += abs_range(a) * T(1e-12);
+    f[0] = (a[4] * a[8] - a[5] * a[7]) / dt;
+    f[1] = (a[2] * a[7] - a[1] * a[8]) / dt;
+    f[2] = (a[1] * a[5] - a[2] * a[4]) / dt;
+    f[3] = (a[5] * a[6] - a[3] * a[8]) / dt;
+    f[4] = (a[0] * a[8] - a[2] * a[6]) / dt;
+    f[5] = (a[3] * a[2] - a[5] * a[0]) / dt;
+    f[6] = (a[7] * a[3] - a[6] * a[4]) / dt;
+    f[7] = (a[6] * a[1] - a[7] * a[0]) / dt;
+    f[8] = (a[0] * a[4] - a[1] * a[3]) / dt;
+  }
+}
+
+// in-place Gauss-Jordan inverse with partial (row) pivoting.  N*N registers.
+template <typename T, int N>
+struct GaussJordan {
+  T a[N][N];
+
+  __device__ __forceinline__ void invert() {
+    int piv[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      T best = tabs(a[k][k]);
+      int p = k;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const T c = tabs(a[i][k]);
+        if (c > best) {
+          best = c;
+          p = i;
+        }
+      }
+      piv[k] = p;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const bool sw = (p == i);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const T lo = a[k][j], hi = a[i][j];
+          a[k][j] = sw ? hi : lo;
+          a[i][j] = sw ? lo : hi;
+        }
+      }
+      const T rp = T(1) / a[k][k];
+      a[k][k] = T(1);
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[k][j] *= rp;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (i == k) continue;
+        const T f = a[i][k];
+        a[i][k] = T(0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[i][j] -= f * a[k][j];
+      }
+    }
+    // (P A)^-1 = A^-1 P^T  ->  undo with column swaps in reverse order
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+#pragma unroll
+      for (int c = k + 1; c < N; ++c) {
+        const bool sw = (piv[k] == c);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const T lo = a[i][k], hi = a[i][c];
+          a[i][k] = sw ? hi : lo;
+          a[i][c] = sw ? lo : hi;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace nfm

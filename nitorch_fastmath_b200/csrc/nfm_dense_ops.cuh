@@ -1,0 +1,135 @@
+// nfm_dense_ops.cuh -- Op structs for dense row-major n x n batches:
+// inverse, determinant, solve (one right-hand side), square matvec.
+#pragma once
+
+#include "nfm_dense_math.cuh"
+#include "nfm_pipeline.cuh"
+#include "nfm_sym_math.cuh"
+
+namespace nfm {
+
+constexpr int kFlagDetRegularise = 1;  // batch_inv n = 2,3: det += range * 1e-12
+
+// LDL^T loaded from the LOWER triangle of a dense matrix (torch.linalg.cholesky
+// with upper=False reads only that triangle, sugar.py:128, :248)
+template <typename T, int N>
+__device__ __forceinline__ void ldl_from_dense_lower(const T (&a)[N * N], LDL<T, N>& f) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) f.w[i][j] = a[j * N + i];
+}
+
+template <typename T, int N, int ALGO>
+struct BatchInvOp {
+  using scalar = T;
+  static constexpr int kLen0 = N * N;
+  static constexpr int kLen1 = 1;
+  static constexpr int kLen2 = 1;
+  static constexpr int kUse = 1;
+  static constexpr int kOut = N * N;
+
+  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&)[1], const T (&)[1], int present,
+                                               int flags, T (&out)[kOut]) {
+    if constexpr (ALGO == NFM_ALGO_LDL) {
+      LDL<T, N> f;
+      ldl_from_dense_lower<T, N>(a, f);
+      f.factor();
+      T packed[packed_len(N)];
+      f.template invert<false>(packed);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) out[i * N + j] = packed[pidx(N, i, j)];
+    } else if constexpr (N <= 3 && ALGO == NFM_ALGO_AUTO) {
+      dense_inv_closed<T, N>(a, flags & kFlagDetRegularise, out);
+    } else {
+      GaussJordan<T, N> g;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) g.a[i][j] = a[i * N + j];
+      g.invert();
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) out[i * N + j] = g.a[i][j];
+    }
+  }
+};
+
+template <typename T, int N>
+struct BatchDetOp {
+  using scalar = T;
+  static constexpr int kLen0 = N * N;
+  static constexpr int kLen1 = 1;
+  static constexpr int kLen2 = 1;
+  static constexpr int kUse = 1;
+  static constexpr int kOut = 1;
+
+  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&)[1], const T (&)[1], int present,
+                                               int flags, T (&out)[1]) {
+    if constexpr (N == 1) out[0] = a[0];
+    else if constexpr (N == 2) out[0] = dense_det2(a);
+    else if constexpr (N == 3) out[0] = dense_det3(a);
+    else {
+      GaussPP<T, N, 0> g;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) g.a[i][j] = a[i * N + j];
+      g.eliminate();
+      out[0] = g.det();
+    }
+  }
+};
+
+// x = A^-1 b, one right-hand side
+template <typename T, int N, int ALGO>
+struct BatchSolveOp {
+  using scalar = T;
+  static constexpr int kLen0 = N * N;
+  static constexpr int kLen1 = N;
+  static constexpr int kLen2 = 1;
+  static constexpr int kUse = 3;
+  static constexpr int kOut = N;
+
+  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&b)[N], const T (&)[1], int present,
+                                               int flags, T (&x)[N]) {
+    if constexpr (ALGO == NFM_ALGO_LDL) {
+      LDL<T, N> f;
+      ldl_from_dense_lower<T, N>(a, f);
+      f.factor();
+      f.solve(b, x);
+    } else {
+      GaussPP<T, N, 1> g;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) g.a[i][j] = a[i * N + j];
+        g.b[i][0] = b[i];
+      }
+      g.eliminate();
+      g.back_substitute();
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = g.b[i][0];
+    }
+  }
+};
+
+template <typename T, int N>
+struct BatchMatvecOp {
+  using scalar = T;
+  static constexpr int kLen0 = N * N;
+  static constexpr int kLen1 = N;
+  static constexpr int kLen2 = 1;
+  static constexpr int kUse = 3;
+  static constexpr int kOut = N;
+
+  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&v)[N], const T (&)[1], int present,
+                                               int flags, T (&y)[N]) {
+    dense_matvec_reg<T, N, N>(a, v, y);
+  }
+};
+
+}  // namespace nfm

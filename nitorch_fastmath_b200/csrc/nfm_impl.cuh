@@ -1,0 +1,40 @@
+// nfm_impl.cuh -- typed implementation entry points.  Each family source
+// (nfm_sym_matvec.cu, nfm_sym_solve.cu, ...) is compiled once per scalar type
+// (-DNFM_SCALAR=float|double) and, for the big families, once per part
+// (-DNFM_PART=k) so the build parallelises; nfm_entry.cu holds the C ABI.
+#pragma once
+
+#include "nfm_common.cuh"
+
+namespace nfm {
+
+template <typename T> int sym_matvec_impl(int n, int layout, const KParams& p, cudaStream_t s);
+
+// sym_solve: part 0 = layouts E, D, F and packed N <= 4 (closed forms);
+// part 1 = packed N 5..10 LDL^T; part 2 = packed N 5..10 pivoted LU
+template <typename T> int sym_solve_part0(int n, int layout, const KParams& p, cudaStream_t s);
+template <typename T> int sym_solve_part1(int n, const KParams& p, cudaStream_t s);
+template <typename T> int sym_solve_part2(int n, const KParams& p, cudaStream_t s);
+
+// sym_invert: part 0 = N <= 4 closed form + N 5..10 LDL^T; part 1 = N 5..10 pivoted LU
+template <typename T> int sym_invert_part0(int n, int diag_only, const KParams& p, cudaStream_t s);
+template <typename T> int sym_invert_part1(int n, int diag_only, const KParams& p, cudaStream_t s);
+
+// dense: part 0 = inverse (closed / Gauss-Jordan), part 1 = inverse (LDL^T) + det + matvec,
+// part 2 = solve LU, part 3 = solve LDL^T
+template <typename T> int batch_inv_lu_impl(int n, const KParams& p, cudaStream_t s);
+template <typename T> int batch_inv_ldl_impl(int n, const KParams& p, cudaStream_t s);
+template <typename T> int batch_det_impl(int n, const KParams& p, cudaStream_t s);
+template <typename T> int batch_matvec_impl(int n, const KParams& p, cudaStream_t s);
+template <typename T> int batch_solve_lu_impl(int n, const KParams& p, cudaStream_t s);
+template <typename T> int batch_solve_ldl_impl(int n, const KParams& p, cudaStream_t s);
+
+// run-time-sized fallbacks (nfm_generic.cu)
+template <typename T>
+int batch_matvec_rt(int m, int n, i64 batch, const void* mat, i64 ms, const void* vec, i64 vs, void* out, i64 os,
+                    cudaStream_t s);
+template <typename T>
+int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out, i64 os,
+                   cudaStream_t s);
+
+}  // namespace nfm

@@ -1,0 +1,161 @@
+// nfm_sym_ops.cuh -- Op structs (see nfm_pipeline.cuh) for the packed-symmetric
+// routines: matvec / addmatvec / submatvec, solve, invert.
+#pragma once
+
+#include "nfm_dense_math.cuh"
+#include "nfm_pipeline.cuh"
+#include "nfm_sym_math.cuh"
+
+namespace nfm {
+
+__host__ __device__ constexpr int layout_len(int layout, int n) {
+  return layout == NFM_LAYOUT_SCALED_IDENTITY ? 1
+         : layout == NFM_LAYOUT_DIAG          ? n
+         : layout == NFM_LAYOUT_SYM           ? packed_len(n)
+                                              : n * n;
+}
+
+constexpr int kFlagSubtract = 1;  // matvec: out = inp - A v
+
+// out = [inp +/-] A v        in0 = mat, in1 = vec, in2 = inp (optional)
+template <typename T, int N, int LAYOUT>
+struct SymMatvecOp {
+  using scalar = T;
+  static constexpr int kLen0 = layout_len(LAYOUT, N);
+  static constexpr int kLen1 = N;
+  static constexpr int kLen2 = N;
+  static constexpr int kUse = 7;
+  static constexpr int kOut = N;
+
+  __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&v)[N], const T (&inp)[N], int present,
+                                               int flags, T (&out)[N]) {
+    T y[N];
+    if constexpr (LAYOUT == NFM_LAYOUT_SCALED_IDENTITY) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = m[0] * v[i];
+    } else if constexpr (LAYOUT == NFM_LAYOUT_DIAG) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = m[i] * v[i];
+    } else if constexpr (LAYOUT == NFM_LAYOUT_SYM) {
+      sym_matvec_reg<T, N>(m, v, y);
+    } else {
+      dense_matvec_reg<T, N, N>(m, v, y);
+    }
+    if (present & 4) {
+      const bool sub = flags & kFlagSubtract;
+#pragma unroll
+      for (int i = 0; i < N; ++i) out[i] = sub ? inp[i] - y[i] : inp[i] + y[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) out[i] = y[i];
+    }
+  }
+};
+
+// x = (A + diag(d))^-1 v      in0 = mat, in1 = vec, in2 = d (optional)
+template <typename T, int N, int LAYOUT, int ALGO>
+struct SymSolveOp {
+  using scalar = T;
+  static constexpr int kLen0 = layout_len(LAYOUT, N);
+  static constexpr int kLen1 = N;
+  static constexpr int kLen2 = N;
+  static constexpr int kUse = 7;
+  static constexpr int kOut = N;
+
+  __device__ static __forceinline__ void apply(const T (&m_in)[kLen0], const T (&v)[N], const T (&reg)[N],
+                                               int present, int flags, T (&x)[N]) {
+    if constexpr (LAYOUT == NFM_LAYOUT_SCALED_IDENTITY) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = v[i] / (m_in[0] + reg[i]);
+    } else if constexpr (LAYOUT == NFM_LAYOUT_DIAG) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = v[i] / (m_in[i] + reg[i]);
+    } else if constexpr (LAYOUT == NFM_LAYOUT_SYM) {
+      T m[kLen0];
+#pragma unroll
+      for (int k = 0; k < kLen0; ++k) m[k] = (k < N) ? m_in[k] + reg[k < N ? k : 0] : m_in[k];
+      if constexpr (N <= 4) {
+        sym_solve_closed<T, N>(m, v, x);
+      } else if constexpr (ALGO == NFM_ALGO_LU) {
+        sym_solve_lu<T, N>(m, v, x);
+      } else {
+        LDL<T, N> f;
+        f.load_packed(m);
+        f.factor();
+        f.solve(v, x);
+      }
+    } else {
+      GaussPP<T, N, 1> g;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) g.a[i][j] = m_in[i * N + j] + (i == j ? reg[i] : T(0));
+        g.b[i][0] = v[i];
+      }
+      g.eliminate();
+      g.back_substitute();
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = g.b[i][0];
+    }
+  }
+};
+
+// out = A^-1 (packed) or diag(A^-1)        in0 = mat
+template <typename T, int N, int ALGO, bool DIAG_ONLY>
+struct SymInvertOp {
+  using scalar = T;
+  static constexpr int kLen0 = packed_len(N);
+  static constexpr int kLen1 = 1;
+  static constexpr int kLen2 = 1;
+  static constexpr int kUse = 1;
+  static constexpr int kOut = DIAG_ONLY ? N : packed_len(N);
+
+  __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&)[1], const T (&)[1], int present,
+                                               int flags, T (&out)[kOut]) {
+    if constexpr (N <= 4) {
+      // reference: N solves against unit vectors = adjugate columns / det
+      T adj[kLen0];
+      const T det = sym_adjugate<T, N>(m, adj);
+#pragma unroll
+      for (int k = 0; k < kOut; ++k) out[k] = adj[k] / det;
+    } else if constexpr (ALGO == NFM_ALGO_LU) {
+      GaussPP<T, N, N> g;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          g.a[i][j] = m[pidx(N, i, j)];
+          g.b[i][j] = (i == j) ? T(1) : T(0);
+        }
+      g.eliminate();
+      g.back_substitute();
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+          if (DIAG_ONLY && j != i) continue;
+          // reference takes entry (j, i) of solve(A, e_i): column i, row j >= i
+          out[DIAG_ONLY ? i : pidx(N, i, j)] = g.b[j][i];
+        }
+    } else {
+      LDL<T, N> f;
+      f.load_packed(m);
+      f.factor();
+      f.template invert<DIAG_ONLY>(out);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// run-time -> compile-time dispatch over N
+// ---------------------------------------------------------------------------
+template <template <int> class OpN, int N_LO, int N_HI>
+struct DispatchN {
+  static int run(int n, const KParams& p, cudaStream_t s) {
+    if (n == N_LO) return run_op<OpN<N_LO>>(p, s);
+    if constexpr (N_LO < N_HI) return DispatchN<OpN, N_LO + 1, N_HI>::run(n, p, s);
+    else return NFM_E_UNSUPPORTED;
+  }
+};
+
+}  // namespace nfm

@@ -1,0 +1,385 @@
+"""Parity of the CUDA path (through the drop-in API -> C ABI) with
+(a) the golden fixtures produced by the real reference and (b) the CPU oracle
+on seeded inputs.  Metric: worst per-matrix norm-wise relative error; bars are
+the north star's 1e-5 (fp32) / 1e-12 (fp64)."""
+import pytest
+import torch
+
+from conftest import TAGS, TOL
+from oracle import generators as G
+from oracle import ref_port as P
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.float64]
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def nfm():
+    import nitorch_fastmath_b200 as pkg
+    from nitorch_fastmath_b200 import _lib
+    _lib.load()
+    return pkg
+
+
+def close(got, want, dtype, rec=1, scale=1.0):
+    assert tuple(got.shape) == tuple(want.shape), (got.shape, want.shape)
+    assert got.dtype == want.dtype
+    err = G.rel_err(got, want, rec)
+    assert err <= TOL[dtype] * scale, f"rel err {err:.3e} > {TOL[dtype] * scale:.1e}"
+
+
+# --------------------------------------------------------------------------
+# golden fixtures (small batch -> strided kernel)
+# --------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", range(1, 11))
+def test_sym_golden(nfm, sym_golden, dtype, n):
+    k = f"{TAGS[dtype]}_n{n}"
+    mat, vec, inp, reg = (sym_golden(f"{k}_{s}", DEV) for s in ("mat", "vec", "inp", "reg"))
+    close(nfm.sym_matvec(mat, vec), sym_golden(f"{k}_matvec"), dtype)
+    close(nfm.sym_addmatvec(inp, mat, vec), sym_golden(f"{k}_addmatvec"), dtype)
+    close(nfm.sym_submatvec(inp, mat, vec), sym_golden(f"{k}_submatvec"), dtype)
+    close(nfm.sym_solve(mat, vec), sym_golden(f"{k}_solve"), dtype)
+    close(nfm.sym_solve(mat, vec, reg), sym_golden(f"{k}_solve_reg"), dtype)
+    close(nfm.sym_solve(mat, vec, method="lu"), sym_golden(f"{k}_solve"), dtype)
+    close(nfm.sym_invert(mat), sym_golden(f"{k}_invert"), dtype)
+    close(nfm.sym_invert(mat, True), sym_golden(f"{k}_invert_diag"), dtype)
+    close(nfm.sym_invert(mat, method="lu"), sym_golden(f"{k}_invert"), dtype)
+    close(nfm.sym_to_full(mat), sym_golden(f"{k}_full"), dtype, 2)
+    # symmetric indefinite: closed forms (n <= 4) / pivoted LU (n > 4), as the reference
+    close(nfm.sym_solve(sym_golden(f"{k}_ind_mat", DEV), vec, method="lu"), sym_golden(f"{k}_ind_solve"), dtype, scale=4)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_eps_golden(nfm, sym_golden, dtype):
+    t = TAGS[dtype]
+    mat, vec = sym_golden(f"{t}_eps2_mat", DEV), sym_golden(f"{t}_eps2_vec", DEV)
+    close(nfm.sym_solve(mat, vec, 0.1), sym_golden(f"{t}_eps2_solve"), dtype)
+    close(nfm.sym_solve(mat, vec, eps=0.1), sym_golden(f"{t}_eps2_solve"), dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", range(1, 11))
+def test_dense_golden(nfm, dense_golden, dtype, n):
+    k = f"{TAGS[dtype]}_n{n}"
+    a, b, s, rhs = (dense_golden(f"{k}_{x}", DEV) for x in ("a", "b", "spd", "rhs"))
+    close(nfm.batchinv(a), dense_golden(f"{k}_inv"), dtype, 2)
+    close(nfm.batchinv(a, method="lu"), dense_golden(f"{k}_inv"), dtype, 2)
+    close(nfm.batchdet(a), dense_golden(f"{k}_det"), dtype, 0)
+    close(nfm.batchmatvec(a, b), dense_golden(f"{k}_matvec"), dtype)
+    close(nfm.solvevec(a, b, "lu"), dense_golden(f"{k}_solve_lu"), dtype)
+    close(nfm.solvevec(s, b, "chol"), dense_golden(f"{k}_solve_chol"), dtype)
+    close(nfm.lmdiv(a, rhs, "lu"), dense_golden(f"{k}_lmdiv_lu"), dtype, 2)
+    close(nfm.lmdiv(s, rhs, "chol"), P.lmdiv(s.cpu(), rhs.cpu(), "chol"), dtype, 2)
+    close(nfm.inv(s, "chol"), dense_golden(f"{k}_inv_chol"), dtype, 2)
+    close(nfm.inv(a, "lu"), dense_golden(f"{k}_inv"), dtype, 2)
+    if n in (2, 3):
+        # the reference's CUDA closed forms, including det += range * 1e-12
+        close(nfm.batchinv(a), dense_golden(f"{k}_closed_inv"), dtype, 2, scale=0.5)
+        close(nfm.batchdet(a), dense_golden(f"{k}_closed_det"), dtype, 0)
+
+
+# --------------------------------------------------------------------------
+# seeded batches large enough for the TMA fast path (+ ragged tail)
+# --------------------------------------------------------------------------
+
+BATCH = 20011   # prime: full tiles + ragged tail for every tile size
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", range(1, 11))
+def test_sym_fast_path_vs_oracle(nfm, dtype, n):
+    from nitorch_fastmath_b200 import _lib
+    mat = G.spd_packed(BATCH, n, dtype, seed=n)
+    vec = G.vectors(BATCH, n, dtype, seed=50 + n)
+    inp = G.vectors(BATCH, n, dtype, seed=90 + n)
+    reg = G.vectors(BATCH, n, dtype, seed=70 + n).abs()
+    dm, dv, di, dr = (t.to(DEV) for t in (mat, vec, inp, reg))
+    x = nfm.sym_solve(dm, dv)
+    assert _lib.load().nfm_last_path_was_tma() == 1
+    close(x, P.sym_solve(mat, vec), dtype)
+    close(nfm.sym_solve(dm, dv, dr), P.sym_solve(mat, vec, reg), dtype)
+    close(nfm.sym_solve(dm, dv, 0.25), P.sym_solve(mat, vec, 0.25), dtype)
+    close(nfm.sym_solve(dm, dv, [0.5, 0.25][:n]), P.sym_solve(mat, vec, [0.5, 0.25][:n]), dtype)
+    close(nfm.sym_solve(dm, dv, method="lu"), P.sym_solve(mat, vec), dtype)
+    close(nfm.sym_matvec(dm, dv), P.sym_matvec(mat, vec), dtype)
+    close(nfm.sym_addmatvec(di, dm, dv), P.sym_addmatvec(inp, mat, vec), dtype)
+    close(nfm.sym_submatvec(di, dm, dv), P.sym_submatvec(inp, mat, vec), dtype)
+    close(nfm.sym_invert(dm), P.sym_invert(mat), dtype)
+    close(nfm.sym_invert(dm, True), P.sym_invert(mat, True), dtype)
+    close(nfm.sym_invert(dm, method="lu"), P.sym_invert(mat), dtype)
+    close(nfm.sym_to_full(dm), P.sym_to_full(mat), dtype, 2)
+    close(nfm.sym_det(dm), torch.det(P.sym_to_full(mat.double())).to(dtype), dtype, 0, scale=10)
+    close(nfm.sym_outer(dv), P.full_to_sym(vec[..., :, None] * vec[..., None, :]), dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", range(1, 11))
+def test_dense_fast_path_vs_oracle(nfm, dtype, n):
+    a = G.dense_shifted(BATCH, n, dtype, seed=n)
+    b = G.vectors(BATCH, n, dtype, seed=30 + n)
+    s = G.dense_spd(BATCH, n, dtype, seed=n)
+    da, db, ds = a.to(DEV), b.to(DEV), s.to(DEV)
+    # reference CPU branch = LAPACK; n <= 3 on CUDA = closed forms: both must hold
+    close(nfm.batchinv(da), P.batchinv(a), dtype, 2)
+    close(nfm.batchdet(da), P.batchdet(a), dtype, 0)
+    close(nfm.batchmatvec(da, db), P.batchmatvec(a, b), dtype)
+    close(nfm.solvevec(da, db), P.solvevec(a, b), dtype)
+    close(nfm.solvevec(ds, db, "chol"), P.solvevec(s, b, "chol"), dtype)
+    close(nfm.inv(ds, "chol"), P.inv(s, "chol"), dtype, 2)
+    if n <= 3:
+        close(nfm.batchinv(da), P.closed_inv(a), dtype, 2, scale=0.5)
+        close(nfm.batchdet(da), P.closed_det(a), dtype, 0)
+
+
+# --------------------------------------------------------------------------
+# semantics: broadcasting, strides, alignment, dtype, in-place, empty, layouts
+# --------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [2, 3, 6, 10])
+def test_broadcasting(nfm, n):
+    dtype = torch.float32
+    mat = G.spd_packed((4, 5), n, dtype, seed=1)
+    vec = G.vectors((4, 5), n, dtype, seed=2)
+    dm, dv = mat.to(DEV), vec.to(DEV)
+    # reference behaviour matrix, SURVEY.md appendix A.4
+    close(nfm.sym_solve(dm, dv[0, 0]), P.sym_solve(mat, vec[0, 0]), dtype)
+    close(nfm.sym_solve(dm[0, 0], dv), P.sym_solve(mat[0, 0], vec), dtype)
+    close(nfm.sym_solve(dm[:1], dv), P.sym_solve(mat[:1], vec), dtype)
+    close(nfm.sym_solve(dm[:, :1], dv[:1]), P.sym_solve(mat[:, :1], vec[:1]), dtype)
+    close(nfm.sym_solve(dm[0, 0], dv[0, 0]), P.sym_solve(mat[0, 0], vec[0, 0]), dtype)
+    # superset: unbatched operand in matvec (the reference's own implementation fails there)
+    want = P.sym_matvec(mat, vec[0, 0].expand(4, 5, n))
+    close(nfm.sym_matvec(dm, dv[0, 0]), want, dtype)
+    # large batch with a broadcast operand goes through the TMA path with stride 0
+    big_m = G.spd_packed(5000, n, dtype, seed=3)
+    v1 = G.vectors(1, n, dtype, seed=4)[0]
+    close(nfm.sym_solve(big_m.to(DEV), v1.to(DEV)), P.sym_solve(big_m, v1), dtype)
+    big_v = G.vectors(5000, n, dtype, seed=5)
+    close(nfm.sym_solve(big_m[0].to(DEV), big_v.to(DEV)), P.sym_solve(big_m[0], big_v), dtype)
+
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_strided_and_unaligned(nfm, n):
+    dtype = torch.float32
+    nn = n * (n + 1) // 2
+    mat = G.spd_packed((7, 900), n, dtype, seed=1)
+    vec = G.vectors((7, 900), n, dtype, seed=2)
+    dm, dv = mat.to(DEV), vec.to(DEV)
+    # transposed batch dims (non-collapsible -> materialised)
+    close(nfm.sym_solve(dm.transpose(0, 1), dv.transpose(0, 1)),
+          P.sym_solve(mat.transpose(0, 1), vec.transpose(0, 1)), dtype)
+    # every second matrix (single non-dense stride -> strided kernel)
+    close(nfm.sym_solve(dm[:, ::2], dv[:, ::2]), P.sym_solve(mat[:, ::2], vec[:, ::2]), dtype)
+    # storage offset that breaks 16-byte alignment
+    flat_m, flat_v = dm.reshape(-1, nn), dv.reshape(-1, n)
+    close(nfm.sym_solve(flat_m[1:], flat_v[1:]), P.sym_solve(mat.reshape(-1, nn)[1:], vec.reshape(-1, n)[1:]), dtype)
+    # non-unit stride in the coefficient dimension
+    wide = torch.zeros(6300, 2 * nn, device=DEV)
+    wide[:, ::2] = flat_m
+    close(nfm.sym_solve(wide[:, ::2], flat_v), P.sym_solve(mat.reshape(-1, nn), vec.reshape(-1, n)), dtype)
+    # coefficient-first storage viewed coefficient-last (what the reference returns, appendix A.4)
+    cf = flat_m.t().contiguous().t()
+    close(nfm.sym_invert(cf), P.sym_invert(mat.reshape(-1, nn)), dtype)
+
+
+def test_dtype_semantics(nfm):
+    mat = G.spd_packed(300, 3, torch.float64, seed=1)
+    vec = G.vectors(300, 3, torch.float32, seed=2)
+    x = nfm.sym_solve(mat.to(DEV), vec.to(DEV))
+    assert x.dtype == torch.float32                      # solve -> vec's dtype (reference)
+    close(x, P.sym_solve(mat, vec), torch.float32)
+    y = nfm.sym_matvec(mat.to(DEV), vec.to(DEV))
+    assert y.dtype == torch.float64                      # matvec -> promoted (reference)
+    close(y, P.sym_matvec(mat, vec.double()), torch.float64)
+    z = nfm.sym_solve(mat.to(DEV), vec.to(DEV), dtype=torch.float64)
+    assert z.dtype == torch.float64
+
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_inplace_variants(nfm, n):
+    dtype = torch.float32
+    mat = G.spd_packed(9000, n, dtype, seed=1)
+    vec = G.vectors(9000, n, dtype, seed=2)
+    inp = G.vectors(9000, n, dtype, seed=3)
+    dm = mat.to(DEV)
+    v = vec.to(DEV)
+    r = nfm.sym_solve_(dm, v)
+    assert r.data_ptr() == v.data_ptr()
+    close(v, P.sym_solve(mat, vec), dtype)
+    i = inp.to(DEV)
+    assert nfm.sym_addmatvec_(i, dm, vec.to(DEV)).data_ptr() == i.data_ptr()
+    close(i, P.sym_addmatvec(inp, mat, vec), dtype)
+    i = inp.to(DEV)
+    nfm.sym_submatvec_(i, dm, vec.to(DEV))
+    close(i, P.sym_submatvec(inp, mat, vec), dtype)
+    m2 = mat.to(DEV)
+    assert nfm.sym_invert_(m2).data_ptr() == m2.data_ptr()
+    close(m2, P.sym_invert(mat), dtype)
+    out = torch.empty(9000, n, device=DEV)
+    assert nfm.sym_solve(dm, vec.to(DEV), out=out) is out
+    close(out, P.sym_solve(mat, vec), dtype)
+
+
+def test_empty_and_unbatched(nfm):
+    mat = G.spd_packed((0, 5), 3, torch.float32)
+    vec = G.vectors((0, 5), 3, torch.float32)
+    assert tuple(nfm.sym_solve(mat.to(DEV), vec.to(DEV)).shape) == (0, 5, 3)
+    assert tuple(nfm.sym_invert(mat.to(DEV)).shape) == (0, 5, 6)
+    assert tuple(nfm.batchinv(torch.zeros(0, 4, 4, device=DEV)).shape) == (0, 4, 4)
+    m1 = G.spd_packed(1, 3, torch.float32)[0]
+    v1 = G.vectors(1, 3, torch.float32)[0]
+    close(nfm.sym_solve(m1.to(DEV), v1.to(DEV)), P.sym_solve(m1, v1), torch.float32)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+def test_compact_layouts(nfm, n):
+    """scaled identity / diagonal / full layouts (reference sym.py:16-24)."""
+    dtype = torch.float64
+    vec = G.vectors(3000, n, dtype, seed=2)
+    dv = vec.to(DEV)
+    sc = 1 + G.vectors(3000, 1, dtype, seed=3).abs()
+    dg = 1 + G.vectors(3000, n, dtype, seed=4).abs()
+    full = P.sym_to_full(G.spd_packed(3000, n, dtype, seed=5))
+    if n > 1:
+        close(nfm.sym_matvec(sc.to(DEV), dv), sc * vec, dtype)
+        close(nfm.sym_solve(sc.to(DEV), dv), vec / sc, dtype)
+        close(nfm.sym_matvec(dg.to(DEV), dv), dg * vec, dtype)
+        close(nfm.sym_solve(dg.to(DEV), dv), vec / dg, dtype)
+        close(nfm.sym_solve(dg.to(DEV), dv, 0.5), vec / (dg + 0.5), dtype)
+        flat = full.reshape(3000, n * n)
+        close(nfm.sym_matvec(flat.to(DEV), dv), P.batchmatvec(full, vec), dtype)
+        close(nfm.sym_solve(flat.to(DEV), dv), P.solvevec(full, vec), dtype)
+
+
+def test_singular_does_not_trap(nfm):
+    # reference: closed forms give NaN/inf for singular input, no exception (appendix A.4)
+    x = nfm.sym_solve(torch.zeros(64, 6, device=DEV), torch.ones(64, 3, device=DEV))
+    assert not torch.isfinite(x).any()
+    x = nfm.sym_solve(torch.zeros(64, 21, device=DEV), torch.ones(64, 6, device=DEV))
+    assert not torch.isfinite(x).any()
+    torch.cuda.synchronize()
+
+
+def test_sym_matmul(nfm):
+    dtype = torch.float64
+    for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1)]:
+        j = G.vectors((2000, k), d, dtype, seed=k * 10 + d)
+        h = G.spd_packed(2000, k, dtype, seed=k)
+        hf = P.sym_to_full(h)
+        if k == d and k <= 3:      # the reference's unrolled branches: J H J^T
+            want = j @ hf @ j.transpose(-1, -2)
+        else:                      # documented: J^T H J
+            want = j.transpose(-1, -2) @ hf @ j
+        close(nfm.sym_matmul(j.to(DEV), h.to(DEV)), P.full_to_sym(want), dtype)
+
+
+# --------------------------------------------------------------------------
+# the reference's own tests/test_batched.py, run on CUDA against this package
+# --------------------------------------------------------------------------
+
+def test_reference_test_batchmatvec(nfm):
+    def check(mat, vec):
+        return torch.allclose(nfm.batchmatvec(mat, vec), mat.matmul(vec.unsqueeze(-1)).squeeze(-1))
+    g = torch.Generator(device=DEV).manual_seed(0)
+    r = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    assert check(r(2, 1, 1), r(2, 2, 1)), "1x1"
+    assert check(r(2, 2, 2), r(2, 2, 2)), "2x2"
+    assert check(r(2, 3, 3), r(2, 2, 3)), "3x3"
+    assert check(r(2, 4, 5), r(2, 2, 5)), "4x5"
+    assert check(r(2, 2, 4, 5), r(5)), "mat longer"
+
+
+def test_reference_test_batchdet_and_inv(nfm):
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for n in (1, 2, 3, 4):
+        mat = torch.randn(2, n, n, device=DEV, generator=g)
+        assert torch.allclose(nfm.batchdet(mat), torch.det(mat.cpu()).to(DEV), rtol=1e-4, atol=1e-6), n
+        mat.diagonal(0, -1, -2).add_(10)
+        assert torch.allclose(nfm.batchinv(mat), torch.linalg.inv(mat.cpu()).to(DEV)), n
+
+
+# --------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs) -- size-independent checks
+# --------------------------------------------------------------------------
+
+def _device_spd(batch, n, dtype, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    a = torch.randn(batch, n, n, device=DEV, dtype=dtype, generator=g)
+    full = a @ a.transpose(-1, -2)
+    full.diagonal(0, -1, -2).add_(n)
+    iu = torch.triu_indices(n, n, 1, device=DEV)
+    return torch.cat([full.diagonal(0, -1, -2), full[..., iu[0], iu[1]]], -1).contiguous()
+
+
+@pytest.mark.parametrize("n,side", [(3, 256), (6, 192), (10, 160)])
+def test_full_size_round_trip(nfm, n, side):
+    """config 2 / 3 / 5: solve then matvec returns the right-hand side;
+    invert(invert(A)) == A; the solve is linear in the right-hand side."""
+    dtype = torch.float32
+    batch = side ** 3
+    mat = _device_spd(batch, n, dtype, seed=n)
+    g = torch.Generator(device=DEV).manual_seed(99)
+    vec = torch.randn(batch, n, device=DEV, dtype=dtype, generator=g)
+    x = nfm.sym_solve(mat, vec)
+    back = nfm.sym_matvec(mat, x)
+    err = ((back - vec).norm(dim=-1) / vec.norm(dim=-1)).max().item()
+    assert err < 2e-5, err
+    x2 = nfm.sym_solve(mat, 2 * vec)
+    assert ((x2 - 2 * x).norm(dim=-1) / x.norm(dim=-1)).max().item() < 1e-6
+    if n <= 6:
+        inv = nfm.sym_invert(mat)
+        again = nfm.sym_invert(inv)
+        assert ((again - mat).norm(dim=-1) / mat.norm(dim=-1)).max().item() < 5e-5
+        # slab parity against the oracle on a slice the CPU finishes in seconds
+        sl = slice(batch // 2, batch // 2 + 50000)
+        close(x[sl], P.sym_solve(mat[sl].cpu(), vec[sl].cpu()), dtype)
+        close(inv[sl], P.sym_invert(mat[sl].cpu()), dtype)
+
+
+def test_config4_dense_fp64(nfm):
+    """config 4 (general 4x4 fp64), at 8M of the 64M batch: A A^-1 = I,
+    det(A^-1) = 1/det(A), solve residual."""
+    n, batch = 4, 8 << 20
+    g = torch.Generator(device=DEV).manual_seed(4)
+    a = torch.randn(batch, n, n, device=DEV, dtype=torch.float64, generator=g)
+    a.diagonal(0, -1, -2).add_(10)
+    b = torch.randn(batch, n, device=DEV, dtype=torch.float64, generator=g)
+    inv = nfm.batchinv(a)
+    eye = torch.eye(n, device=DEV, dtype=torch.float64)
+    assert (a @ inv - eye).abs().max().item() < 1e-13
+    d, di = nfm.batchdet(a), nfm.batchdet(inv)
+    assert (d * di - 1).abs().max().item() < 1e-12
+    x = nfm.solvevec(a, b)
+    assert ((a @ x[..., None])[..., 0] - b).abs().max().item() < 1e-12
+    sl = slice(12345, 12345 + 100000)
+    close(inv[sl], P.batchinv(a[sl].cpu()), torch.float64, 2)
+    close(d[sl], P.batchdet(a[sl].cpu()), torch.float64, 0)
+    close(x[sl], P.solvevec(a[sl].cpu(), b[sl].cpu()), torch.float64)
+
+
+# --------------------------------------------------------------------------
+# host-resident operands: the chunked H2D / kernel / D2H pipeline
+# --------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_host_pipeline(nfm, n):
+    dtype = torch.float32
+    batch = 1_000_003
+    mat = G.spd_packed(batch, n, dtype, seed=1).pin_memory()
+    vec = G.vectors(batch, n, dtype, seed=2).pin_memory()
+    x = nfm.sym_solve(mat, vec)
+    assert x.device.type == "cpu"
+    xd = nfm.sym_solve(mat.to(DEV), vec.to(DEV)).cpu()
+    assert torch.equal(x, xd)
+    sl = slice(500_000, 520_000)
+    close(x[sl], P.sym_solve(mat[sl], vec[sl]), dtype)
+    inv = nfm.sym_invert(mat)
+    assert torch.equal(inv, nfm.sym_invert(mat.to(DEV)).cpu())
+    y = nfm.sym_matvec(mat, vec)
+    assert torch.equal(y, nfm.sym_matvec(mat.to(DEV), vec.to(DEV)).cpu())
+    # non-plain host operands take the whole-upload path
+    close(nfm.sym_solve(mat[:1000, :], vec[0]), P.sym_solve(mat[:1000], vec[0]), dtype)
