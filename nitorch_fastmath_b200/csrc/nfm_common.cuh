@@ -106,6 +106,10 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// programmatic dependent launch (PDL)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------
 // record movers: a record is L contiguous elements of T.  Within a staged tile
 // record r starts at r*L*sizeof(T) from a 16-byte aligned base, so its

@@ -132,4 +132,10 @@ struct BatchMatvecOp {
   }
 };
 
+// measured optima (profiles/r1_tile_geometry_sweep.txt): fp64 pivoted elimination
+// wants more resident warps than the one-big-CTA rule gives
+template <> struct Tune<BatchInvOp<double, 4, NFM_ALGO_AUTO>> : TuneFixed<BatchInvOp<double, 4, NFM_ALGO_AUTO>, 256, 256, 3> {};
+template <> struct Tune<BatchDetOp<double, 4>> : TuneFixed<BatchDetOp<double, 4>, 256, 128, 3> {};
+template <> struct Tune<BatchSolveOp<double, 4, NFM_ALGO_LU>> : TuneFixed<BatchSolveOp<double, 4, NFM_ALGO_LU>, 128, 128, 3> {};
+
 }  // namespace nfm

@@ -36,6 +36,12 @@ const DeviceInfo& device_info() {
   return cache[dev];
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 namespace {
 
 int fail(int code, const char* what) {

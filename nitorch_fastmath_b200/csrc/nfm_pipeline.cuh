@@ -1,16 +1,27 @@
 // nfm_pipeline.cuh -- the two kernels every op runs through.
 //
-//   tile_kernel<Op, THREADS, MPT, STAGES>  (fast path)
+//   tile_kernel<Op, THREADS, MPT, STAGES, SEG>  (fast path)
 //     Persistent CTAs, one thread per matrix (MPT matrices per thread per
 //     tile).  The AoS records (coefficient dimension last) of a tile of
 //     TILE = THREADS*MPT consecutive matrices are one contiguous byte range
-//     per operand, so each operand tile moves HBM -> shared memory with ONE
-//     1-D TMA bulk copy (cp.async.bulk, completion on an mbarrier) into a
+//     per operand, so each operand tile moves HBM -> shared memory with 1-D
+//     TMA bulk copies (cp.async.bulk, completion on an mbarrier) into a
 //     STAGES-deep ring; threads pull their own record out of shared memory
 //     with the widest conflict-free access, compute in registers, stage the
-//     result record in shared memory and one thread sends the whole output
-//     tile back with a TMA bulk store.  Every HBM access is therefore a full,
-//     aligned, contiguous burst regardless of the record length.
+//     result record in shared memory and the tile goes back with TMA bulk
+//     stores.  Every HBM access is therefore a full, aligned, contiguous
+//     burst regardless of the record length.
+//
+//     SEG = false: one bulk copy per operand per tile, record r of the tile at
+//       r * record_bytes.  Conflict free whenever record_bytes is an odd
+//       multiple of its widest access (all packed-symmetric sizes but two).
+//     SEG = true: for records that are a multiple of 32 B (dense 4x4, ...),
+//       where consecutive threads would hit the same banks 2..8-way: the tile
+//       is cut into 8 segments, each landing 16 B further than a dense layout
+//       would put it (8 bulk copies per operand, issued by 8 lanes), and
+//       thread m takes record (m / 8) of segment (m % 8).  The 8 lanes of a
+//       128-bit shared-memory phase then sit in 8 different segments, i.e. 8
+//       different 16 B bank groups: conflict free for every record size.
 //
 //   strided_kernel<Op>  (general path)
 //     One thread per matrix straight from global memory with arbitrary batch
@@ -37,18 +48,34 @@ extern std::atomic<unsigned long long> g_launch_count;
 extern thread_local int t_last_path_tma;
 void set_error(const char* fmt, ...);
 
-constexpr int round16(int x) { return (x + 15) & ~15; }
+constexpr int kSegs = 8;     // segments per tile in the SEG layout
+constexpr int kSegPad = 16;  // bytes of skew per segment
 
-template <class Op, int THREADS, int MPT>
+template <class Op, int THREADS, int MPT, bool SEG>
 struct TileGeom {
   using T = typename Op::scalar;
   static constexpr int kTile = THREADS * MPT;
-  static constexpr int kBytes0 = kTile * Op::kLen0 * int(sizeof(T));
-  static constexpr int kBytes1 = kTile * Op::kLen1 * int(sizeof(T));
-  static constexpr int kBytes2 = kTile * Op::kLen2 * int(sizeof(T));
-  static constexpr int kBytesOut = kTile * Op::kOut * int(sizeof(T));
+  static constexpr int kPad = SEG ? kSegs * kSegPad : 0;
+  // payload bytes of one operand tile / its footprint in shared memory
+  static constexpr int bytes(int len) { return kTile * len * int(sizeof(T)); }
+  static constexpr int footprint(int len) { return bytes(len) + kPad; }
+  static constexpr int kBytes0 = bytes(Op::kLen0), kBytes1 = bytes(Op::kLen1), kBytes2 = bytes(Op::kLen2);
+  static constexpr int kBytesOut = bytes(Op::kOut);
+  static constexpr int kFootOut = footprint(Op::kOut);
+  static_assert(kTile % 64 == 0, "tile must be a multiple of 64 matrices");
   static_assert(kBytes0 % 16 == 0 && kBytes1 % 16 == 0 && kBytes2 % 16 == 0 && kBytesOut % 16 == 0,
                 "tile byte counts must be multiples of 16 for TMA bulk copies");
+
+  // byte offset of record m (0 <= m < kTile, in thread order) inside an operand tile
+  template <int LEN>
+  __device__ static __forceinline__ int rec_offset(int m) {
+    if constexpr (SEG) {
+      constexpr int seg_bytes = bytes(LEN) / kSegs;
+      return (m & (kSegs - 1)) * (seg_bytes + kSegPad) + (m >> 3) * LEN * int(sizeof(T));
+    } else {
+      return m * LEN * int(sizeof(T));
+    }
+  }
 };
 
 // which operands are staged through shared memory for this launch:
@@ -61,22 +88,58 @@ __host__ __device__ inline int staged_mask(const KParams& p) {
   return m;
 }
 
-template <class Op, int THREADS, int MPT, int STAGES>
+// element e (0 <= e < count*LEN, tile-global order) -> byte offset in the staged tile
+template <class G, int LEN>
+__device__ __forceinline__ int elem_offset(int e) {
+  using T = typename G::T;
+  if constexpr (G::kPad != 0) {
+    constexpr int per_seg = G::kTile / kSegs * LEN;  // elements per segment
+    const int seg = e / per_seg;
+    return seg * (per_seg * int(sizeof(T)) + kSegPad) + (e - seg * per_seg) * int(sizeof(T));
+  } else {
+    return e * int(sizeof(T));
+  }
+}
+
+// ragged last tile: all threads copy `count` records between global memory and
+// the staged layout with plain coalesced accesses
+template <class G, int LEN>
+__device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typename G::T* src, int count) {
+  using T = typename G::T;
+  for (int e = threadIdx.x; e < count * LEN; e += blockDim.x)
+    *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e)) = src[e];
+}
+
+template <class G, int LEN>
+__device__ __forceinline__ void coop_store(typename G::T* dst, const unsigned char* smem_tile, int count) {
+  using T = typename G::T;
+  for (int e = threadIdx.x; e < count * LEN; e += blockDim.x)
+    dst[e] = *reinterpret_cast<const T*>(smem_tile + elem_offset<G, LEN>(e));
+}
+
+template <class Op, int THREADS, int MPT, int STAGES, bool SEG>
 __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ KParams p, const i64 ntiles) {
+  // ntiles = number of FULL tiles (moved by TMA).  A ragged last tile of
+  // rem = p.batch - ntiles*TILE matrices is handled by the CTA whose turn it
+  // is, with a cooperative guarded copy in place of the bulk copies.
   using T = typename Op::scalar;
-  using G = TileGeom<Op, THREADS, MPT>;
+  using G = TileGeom<Op, THREADS, MPT, SEG>;
   constexpr int TILE = G::kTile;
+  const int rem = int(p.batch - ntiles * TILE);
+  const i64 ntiles_all = ntiles + (rem > 0 ? 1 : 0);
+  constexpr int kIssuers = SEG ? kSegs : 1;  // threads that issue bulk copies (one segment each)
 
   extern __shared__ __align__(128) unsigned char smem[];
   const int staged = staged_mask(p);
-  const int b0 = (staged & 1) ? G::kBytes0 : 0;
-  const int b1 = (staged & 2) ? G::kBytes1 : 0;
-  const int b2 = (staged & 4) ? G::kBytes2 : 0;
-  const int stage_bytes = b0 + b1 + b2;
+  const int f0 = (staged & 1) ? G::footprint(Op::kLen0) : 0;
+  const int f1 = (staged & 2) ? G::footprint(Op::kLen1) : 0;
+  const int f2 = (staged & 4) ? G::footprint(Op::kLen2) : 0;
+  const int stage_bytes = f0 + f1 + f2;
+  const uint32_t tx_bytes = ((staged & 1) ? G::kBytes0 : 0) + ((staged & 2) ? G::kBytes1 : 0) + ((staged & 4) ? G::kBytes2 : 0);
 
   unsigned char* const in_base = smem;
   unsigned char* const out_base = smem + STAGES * stage_bytes;
-  uint64_t* const full = reinterpret_cast<uint64_t*>(out_base + 2 * G::kBytesOut);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(out_base + 2 * G::kFootOut);
 
   const int tid = threadIdx.x;
   const T* const g0 = static_cast<const T*>(p.in[0].ptr);
@@ -89,22 +152,40 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
-    policy = policy_evict_first();
   }
+  if (tid < kIssuers) policy = policy_evict_first();
   __syncthreads();
+  // programmatic dependent launch: everything above overlapped the previous
+  // kernel's tail; its results are visible only after this wait
+  grid_dependency_wait();
+  grid_launch_dependents();
 
-  // producer: one elected thread arms the stage barrier with the byte count
-  // and issues one bulk copy per staged operand
+  // producer (threads 0..kIssuers-1): thread 0 arms the stage barrier with the
+  // tile's byte count; each issuer sends its segment of every staged operand
   auto issue = [&](int stage, i64 tile) {
     unsigned char* dst = in_base + stage * stage_bytes;
     const i64 first = tile * TILE;
-    mbar_arrive_expect_tx(&full[stage], uint32_t(stage_bytes));
-    if (staged & 1) bulk_g2s(dst, g0 + first * Op::kLen0, G::kBytes0, &full[stage], policy);
-    if (staged & 2) bulk_g2s(dst + b0, g1 + first * Op::kLen1, G::kBytes1, &full[stage], policy);
-    if (staged & 4) bulk_g2s(dst + b0 + b1, g2 + first * Op::kLen2, G::kBytes2, &full[stage], policy);
+    if (tid == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
+    constexpr int nseg = SEG ? kSegs : 1;
+    const int seg = SEG ? tid : 0;
+    if (staged & 1) {
+      constexpr int sb = G::kBytes0 / nseg;
+      bulk_g2s(dst + seg * (sb + (SEG ? kSegPad : 0)), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb,
+               sb, &full[stage], policy);
+    }
+    if (staged & 2) {
+      constexpr int sb = G::kBytes1 / nseg;
+      bulk_g2s(dst + f0 + seg * (sb + (SEG ? kSegPad : 0)),
+               reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb, sb, &full[stage], policy);
+    }
+    if (staged & 4) {
+      constexpr int sb = G::kBytes2 / nseg;
+      bulk_g2s(dst + f0 + f1 + seg * (sb + (SEG ? kSegPad : 0)),
+               reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb, sb, &full[stage], policy);
+    }
   };
 
-  if (tid == 0) {
+  if (tid < kIssuers) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       const i64 t = i64(blockIdx.x) + i64(s) * gridDim.x;
@@ -113,13 +194,23 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
   }
 
   int it = 0;
-  for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  for (i64 tile = blockIdx.x; tile < ntiles_all; tile += gridDim.x, ++it) {
     const int stage = it % STAGES;
     const uint32_t parity = uint32_t(it / STAGES) & 1u;
-    const unsigned char* sin = in_base + stage * stage_bytes;
-    T* sout = reinterpret_cast<T*>(out_base + (it & 1) * G::kBytesOut);
+    unsigned char* sin = in_base + stage * stage_bytes;
+    unsigned char* sout = out_base + (it & 1) * G::kFootOut;
+    const bool ragged = tile >= ntiles;  // at most once, as this CTA's last tile
 
-    mbar_wait(&full[stage], parity);
+    if (!ragged) {
+      mbar_wait(&full[stage], parity);
+    } else {
+      // no bulk copy was issued into this stage: fill it by hand in the same layout
+      const i64 first = tile * TILE;
+      if (staged & 1) coop_load<G, Op::kLen0>(sin, g0 + first * Op::kLen0, rem);
+      if (staged & 2) coop_load<G, Op::kLen1>(sin + f0, g1 + first * Op::kLen1, rem);
+      if (staged & 4) coop_load<G, Op::kLen2>(sin + f0 + f1, g2 + first * Op::kLen2, rem);
+      __syncthreads();
+    }
 
     // staged operands come out of shared memory; broadcast (stride 0) operands
     // are one record for the whole batch, re-read through L1; absent ones are 0
@@ -127,22 +218,22 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       const int m = tid + j * THREADS;
-      if (staged & 1) load_record(reinterpret_cast<const T*>(sin) + m * Op::kLen0, r0[j]);
+      if (staged & 1) load_record(reinterpret_cast<const T*>(sin + G::template rec_offset<Op::kLen0>(m)), r0[j]);
       else if (p.present & 1) load_record_scalar(g0, r0[j]);
       else zero_record(r0[j]);
-      if (staged & 2) load_record(reinterpret_cast<const T*>(sin + b0) + m * Op::kLen1, r1[j]);
+      if (staged & 2) load_record(reinterpret_cast<const T*>(sin + f0 + G::template rec_offset<Op::kLen1>(m)), r1[j]);
       else if (p.present & 2) load_record_scalar(g1, r1[j]);
       else zero_record(r1[j]);
-      if (staged & 4) load_record(reinterpret_cast<const T*>(sin + b0 + b1) + m * Op::kLen2, r2[j]);
+      if (staged & 4) load_record(reinterpret_cast<const T*>(sin + f0 + f1 + G::template rec_offset<Op::kLen2>(m)), r2[j]);
       else if (p.present & 4) load_record_scalar(g2, r2[j]);
       else zero_record(r2[j]);
     }
 
     // the output buffer we are about to overwrite was last read by the bulk
-    // store issued two tiles ago: allow one store still pending
-    if (tid == 0) bulk_wait_read<1>();
+    // store issued two tiles ago: allow one store (group) still pending
+    if (tid < kIssuers) bulk_wait_read<1>();
     __syncthreads();  // every thread has its inputs in registers: stage is free
-    if (tid == 0) {
+    if (tid < kIssuers) {
       const i64 nxt = tile + i64(STAGES) * gridDim.x;
       if (nxt < ntiles) issue(stage, nxt);
     }
@@ -151,16 +242,25 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
     for (int j = 0; j < MPT; ++j) {
       T o[Op::kOut];
       Op::apply(r0[j], r1[j], r2[j], p.present, p.flags, o);
-      store_record(sout + (tid + j * THREADS) * Op::kOut, o);
+      store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(tid + j * THREADS)), o);
+    }
+    if (ragged) {
+      __syncthreads();
+      coop_store<G, Op::kOut>(gout + tile * TILE * Op::kOut, sout, rem);
+      break;
     }
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(gout + tile * TILE * Op::kOut, sout, G::kBytesOut);
+    if (tid < kIssuers) {
+      constexpr int nseg = SEG ? kSegs : 1;
+      constexpr int sb = G::kBytesOut / nseg;
+      const int seg = SEG ? tid : 0;
+      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * TILE * Op::kOut) + seg * sb,
+               sout + seg * (sb + (SEG ? kSegPad : 0)), sb);
       bulk_commit();
     }
   }
-  if (tid == 0) bulk_wait<0>();
+  if (tid < kIssuers) bulk_wait<0>();
 }
 
 template <class Op>
@@ -170,6 +270,8 @@ __global__ void __launch_bounds__(128) strided_kernel(const __grid_constant__ KP
   const T* const g1 = static_cast<const T*>(p.in[1].ptr);
   const T* const g2 = static_cast<const T*>(p.in[2].ptr);
   T* const gout = static_cast<T*>(p.out);
+  grid_dependency_wait();
+  grid_launch_dependents();
   for (i64 b = i64(blockIdx.x) * blockDim.x + threadIdx.x; b < p.batch; b += i64(gridDim.x) * blockDim.x) {
     T r0[Op::kLen0], r1[Op::kLen1], r2[Op::kLen2], o[Op::kOut];
     zero_record(r0);
@@ -191,47 +293,141 @@ struct DeviceInfo {
   int max_smem_optin;
 };
 const DeviceInfo& device_info();  // cached per current device
+int current_device();
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Default tile geometry.  Targets (DESIGN.md "tile geometry"): >= ~16 KB of
-// input per stage so that 2 resident CTAs x (STAGES-1) stages keep > 64 KB of
-// loads in flight per SM; <= ~100 KB of shared memory per CTA so two CTAs fit.
+// Tile geometry.  Measured on B200 (profiles/r1_tile_geometry_sweep.txt): the
+// best configurations keep ONE large CTA per SM with 2 (big records) or 3
+// stages and ~130-150 KB of shared memory -- large bulk copies beat many small
+// ones -- so the rule is: stages = 2 when a matrix moves >= 100 B, else 3;
+// TILE = the largest of {64,128,256,384,512,768,1024} whose ring (mandatory
+// operands) + double-buffered output fits 152 KB; THREADS = 512 / 384 / 256 /
+// TILE.  Optional operands (regulariser, addend) grow the ring up to the
+// 227 KB limit.  TuneFixed pins ops whose measured optimum differs.
+// -DNFM_TUNE_TILE / NFM_TUNE_THREADS / NFM_TUNE_STAGES / NFM_TUNE_SEG override
+// the rule for tuning builds.
 template <class Op>
-struct Tune {
+struct TuneBase {
   using T = typename Op::scalar;
-  static constexpr int kInBytes = (((Op::kUse >> 0) & 1) * Op::kLen0 + ((Op::kUse >> 1) & 1) * Op::kLen1 +
-                                   ((Op::kUse >> 2) & 1) * Op::kLen2) * int(sizeof(T));
+  // operand 2 is the optional one in every op that has it
+  static constexpr int kInBytes = (((Op::kUse >> 0) & 1) * Op::kLen0 + ((Op::kUse >> 1) & 1) * Op::kLen1) * int(sizeof(T));
   static constexpr int kOutBytes = Op::kOut * int(sizeof(T));
-  static constexpr int kRec = kInBytes + kOutBytes;
-  // matrices per tile: aim at ~24 KB of input per stage, clamp to [64, 1024]
-  static constexpr int kWant = 24576 / (kInBytes > 0 ? kInBytes : 1);
-  static constexpr int kTile = kWant >= 1024 ? 1024 : kWant >= 512 ? 512 : kWant >= 256 ? 256 : kWant >= 128 ? 128 : 64;
-  static constexpr int kThreads = kTile >= 256 ? 256 : kTile;
-  static constexpr int kMpt = kTile / kThreads;
-  static constexpr int kStages = 3;
+  // records that are a multiple of 32 B bank-conflict in the dense layout
+  static constexpr bool conflicts(int len) { return (len * int(sizeof(T))) % 32 == 0; }
+#ifdef NFM_TUNE_SEG
+  static constexpr bool kSeg = NFM_TUNE_SEG;
+#else
+  static constexpr bool kSeg = (((Op::kUse >> 0) & 1) && conflicts(Op::kLen0)) || (((Op::kUse >> 1) & 1) && conflicts(Op::kLen1)) ||
+                               conflicts(Op::kOut);
+#endif
 };
 
-template <class Op, int THREADS, int MPT, int STAGES>
+constexpr int kSmemTarget = 152 * 1024;
+
+constexpr int pick_tile(int stages, int in_bytes, int out_bytes) {
+  const int per_matrix = stages * in_bytes + 2 * out_bytes;
+  const int cands[7] = {1024, 768, 512, 384, 256, 128, 64};
+  for (int i = 0; i < 7; ++i)
+    if (cands[i] * per_matrix <= kSmemTarget) return cands[i];
+  return 64;
+}
+
+constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile == 512 ? 256 : tile; }
+
+template <class Op>
+struct TuneRule : TuneBase<Op> {
+  using B = TuneBase<Op>;
+#ifdef NFM_TUNE_STAGES
+  static constexpr int kStages = NFM_TUNE_STAGES;
+#else
+  static constexpr int kStages = (B::kInBytes + B::kOutBytes >= 100) ? 2 : 3;
+#endif
+#ifdef NFM_TUNE_TILE
+  static constexpr int kTile = NFM_TUNE_TILE;
+#else
+  static constexpr int kTile = pick_tile(kStages, B::kInBytes, B::kOutBytes);
+#endif
+#ifdef NFM_TUNE_THREADS
+  static constexpr int kThreads = NFM_TUNE_THREADS < kTile ? NFM_TUNE_THREADS : kTile;
+#else
+  static constexpr int kThreads = pick_threads(kTile);
+#endif
+  static constexpr int kMpt = kTile / kThreads;
+};
+
+template <class Op, int TILE, int THREADS, int STAGES>
+struct TuneFixed : TuneBase<Op> {
+#if defined(NFM_TUNE_TILE) || defined(NFM_TUNE_THREADS) || defined(NFM_TUNE_STAGES)
+  static constexpr int kTile = TuneRule<Op>::kTile, kThreads = TuneRule<Op>::kThreads, kStages = TuneRule<Op>::kStages;
+#else
+  static constexpr int kTile = TILE, kThreads = THREADS, kStages = STAGES;
+#endif
+  static constexpr int kMpt = kTile / kThreads;
+};
+
+template <class Op>
+struct Tune : TuneRule<Op> {};
+
+// Launch with programmatic stream serialization: the kernel may become resident
+// while the previous kernel in the stream drains; it touches global memory only
+// after griddepcontrol.wait, so ordering is unchanged.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// per (kernel instantiation, device, staged mask): resident CTAs per SM, 0 = not yet known
+struct LaunchCache {
+  std::atomic<int> per_sm[16][8];
+  std::atomic<int> attr_set[16];
+};
+
+template <class Op, int THREADS, int MPT, int STAGES, bool SEG>
 int launch_tile(const KParams& p, i64 ntiles, cudaStream_t stream) {
-  using G = TileGeom<Op, THREADS, MPT>;
-  auto kern = tile_kernel<Op, THREADS, MPT, STAGES>;
+  using G = TileGeom<Op, THREADS, MPT, SEG>;
+  static LaunchCache cache;  // zero-initialised
+  auto kern = tile_kernel<Op, THREADS, MPT, STAGES, SEG>;
   const int staged = staged_mask(p);
-  const int stage_bytes = ((staged & 1) ? G::kBytes0 : 0) + ((staged & 2) ? G::kBytes1 : 0) + ((staged & 4) ? G::kBytes2 : 0);
-  const int smem = STAGES * stage_bytes + 2 * G::kBytesOut + STAGES * 8 + 16;
+  auto smem_for = [](int mask) {
+    const int stage = ((mask & 1) ? G::footprint(Op::kLen0) : 0) + ((mask & 2) ? G::footprint(Op::kLen1) : 0) +
+                      ((mask & 4) ? G::footprint(Op::kLen2) : 0);
+    return STAGES * stage + 2 * G::kFootOut + STAGES * 8 + 16;
+  };
+  const int smem = smem_for(staged);
   const DeviceInfo& dev = device_info();
   if (smem > dev.max_smem_optin) return -1;  // caller falls back to the strided kernel
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return int(e);
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-  if (e != cudaSuccess) return int(e);
-  if (per_sm < 1) return -1;
+  const int d = current_device() & 15;
+  if (!cache.attr_set[d].load(std::memory_order_acquire)) {
+    int most = smem_for(Op::kUse & 7);
+    if (most > dev.max_smem_optin) most = dev.max_smem_optin;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    if (e != cudaSuccess) return int(e);
+    cache.attr_set[d].store(1, std::memory_order_release);
+  }
+  int per_sm = cache.per_sm[d][staged].load(std::memory_order_acquire);
+  if (per_sm == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+    if (e != cudaSuccess) return int(e);
+    if (per_sm < 1) return -1;
+    cache.per_sm[d][staged].store(per_sm, std::memory_order_release);
+  }
+  const i64 ntiles_all = ntiles + (p.batch > ntiles * G::kTile ? 1 : 0);
   i64 grid = i64(dev.sm_count) * per_sm;
-  if (grid > ntiles) grid = ntiles;
-  kern<<<unsigned(grid), THREADS, smem, stream>>>(p, ntiles);
+  if (grid > ntiles_all) grid = ntiles_all;
+  cudaError_t e = launch_pdl(kern, unsigned(grid), THREADS, size_t(smem), stream, p, ntiles);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return int(cudaGetLastError());
+  return int(e);
 }
 
 template <class Op>
@@ -241,22 +437,21 @@ int launch_strided(const KParams& p, cudaStream_t stream) {
   i64 blocks = (p.batch + 127) / 128;
   const i64 cap = i64(dev.sm_count) * 16;
   if (blocks > cap) blocks = cap;
-  strided_kernel<Op><<<unsigned(blocks), 128, 0, stream>>>(p);
+  cudaError_t e = launch_pdl(strided_kernel<Op>, unsigned(blocks), 128, size_t(0), stream, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return int(cudaGetLastError());
+  return int(e);
 }
 
 // Run an op over p.batch matrices: TMA-staged tiles for the bulk when every
 // operand is dense-or-broadcast and 16 B aligned, strided kernel for the rest.
 template <class Op>
 int run_op(KParams p, cudaStream_t stream) {
-  using T = typename Op::scalar;
   using Tn = Tune<Op>;
   constexpr int TILE = Tn::kThreads * Tn::kMpt;
   t_last_path_tma = 0;
   if (p.batch == 0) return NFM_OK;
   const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2};
-  bool fast = p.batch >= TILE && p.out_stride == Op::kOut && aligned16(p.out);
+  bool fast = p.out_stride == Op::kOut && aligned16(p.out);
   int nstaged = 0;
   for (int i = 0; i < kMaxIn && fast; ++i) {
     if (!((p.present >> i) & 1)) continue;
@@ -266,18 +461,13 @@ int run_op(KParams p, cudaStream_t stream) {
   }
   if (fast && nstaged == 0) fast = false;
   if (fast) {
-    const i64 ntiles = p.batch / TILE;
-    int rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages>(p, ntiles, stream);
+    // full tiles by TMA, the ragged remainder inside the same launch
+    int rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, p.batch / TILE, stream);
     if (rc == 0) {
       t_last_path_tma = 1;
-      const i64 done = ntiles * TILE;
-      if (done == p.batch) return NFM_OK;
-      // ragged tail through the strided kernel
-      for (int i = 0; i < kMaxIn; ++i)
-        if ((p.present >> i) & 1) p.in[i].ptr = static_cast<const T*>(p.in[i].ptr) + done * p.in[i].stride;
-      p.out = static_cast<T*>(p.out) + done * p.out_stride;
-      p.batch -= done;
-    } else if (rc > 0) {
+      return NFM_OK;
+    }
+    if (rc > 0) {
       set_error("tile kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
       return rc;
     }

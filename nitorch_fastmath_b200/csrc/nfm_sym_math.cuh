@@ -248,7 +248,7 @@ struct GaussPP {
     det_sign = T(1);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      if constexpr (true) {
+      {
         // pivot search: first row of maximal |a_ik|, i >= k  (LAPACK getrf / idamax)
         T best = tabs(a[k][k]);
         int p = k;

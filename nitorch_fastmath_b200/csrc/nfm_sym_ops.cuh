@@ -119,23 +119,20 @@ struct SymInvertOp {
 #pragma unroll
       for (int k = 0; k < kOut; ++k) out[k] = adj[k] / det;
     } else if constexpr (ALGO == NFM_ALGO_LU) {
-      GaussPP<T, N, N> g;
+      // in-place Gauss-Jordan with partial pivoting on the expanded matrix
+      GaussJordan<T, N> g;
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          g.a[i][j] = m[pidx(N, i, j)];
-          g.b[i][j] = (i == j) ? T(1) : T(0);
-        }
-      g.eliminate();
-      g.back_substitute();
+        for (int j = 0; j < N; ++j) g.a[i][j] = m[pidx(N, i, j)];
+      g.invert();
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = i; j < N; ++j) {
           if (DIAG_ONLY && j != i) continue;
           // reference takes entry (j, i) of solve(A, e_i): column i, row j >= i
-          out[DIAG_ONLY ? i : pidx(N, i, j)] = g.b[j][i];
+          out[DIAG_ONLY ? i : pidx(N, i, j)] = g.a[j][i];
         }
     } else {
       LDL<T, N> f;

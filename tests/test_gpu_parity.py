@@ -147,6 +147,45 @@ def test_dense_fast_path_vs_oracle(nfm, dtype, n):
         close(nfm.batchdet(da), P.closed_det(a), dtype, 0)
 
 
+@pytest.mark.parametrize("batch", [1, 2, 63, 64, 1023, 1024, 1025, 2 * 1024 + 17, 148 * 1024 + 5])
+def test_ragged_tile_boundaries(nfm, batch):
+    """Batches around the tile size: full tiles go by TMA, the ragged remainder is
+    finished inside the same launch (cooperative copy) -- 3x3 fp32 (tile 1024),
+    6x6 fp32 (tile 512), dense 4x4 fp64 (segmented layout, tile 256)."""
+    from nitorch_fastmath_b200 import _lib
+    for n in (3, 6):
+        mat = G.spd_packed(batch, n, torch.float32, seed=batch + n)
+        vec = G.vectors(batch, n, torch.float32, seed=batch + n + 1)
+        before = _lib.launch_count()
+        x = nfm.sym_solve(mat.to(DEV), vec.to(DEV))
+        assert _lib.launch_count() - before == 1 and _lib.load().nfm_last_path_was_tma() == 1
+        close(x, P.sym_solve(mat, vec), torch.float32)
+        close(nfm.sym_invert(mat.to(DEV)), P.sym_invert(mat), torch.float32)
+    a = G.dense_shifted(batch, 4, torch.float64, seed=batch)
+    b = G.vectors(batch, 4, torch.float64, seed=batch + 1)
+    close(nfm.batchinv(a.to(DEV)), P.batchinv(a), torch.float64, 2)
+    close(nfm.batchdet(a.to(DEV)), P.batchdet(a), torch.float64, 0)
+    close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), torch.float64)
+
+
+def test_back_to_back_launches_are_ordered(nfm):
+    """Kernels are launched with programmatic stream serialization (they may
+    become resident while the previous one drains); a chain of dependent
+    in-place calls must still see each other's results."""
+    n = 3
+    mat = G.spd_packed(300_000, n, torch.float64, seed=1)
+    vec = G.vectors(300_000, n, torch.float64, seed=2)
+    dm, v = mat.to(DEV), vec.to(DEV)
+    for _ in range(8):                      # x <- A^-1 x ; x <- A x   (8 round trips, 16 dependent launches)
+        nfm.sym_solve_(dm, v)
+        nfm.sym_matvec(dm, v, out=v)
+    close(v, vec, torch.float64, scale=100)
+    acc = torch.zeros_like(v)
+    for _ in range(10):
+        nfm.sym_addmatvec_(acc, dm, v)
+    close(acc, 10 * P.sym_matvec(mat, vec), torch.float64, scale=100)
+
+
 # --------------------------------------------------------------------------
 # semantics: broadcasting, strides, alignment, dtype, in-place, empty, layouts
 # --------------------------------------------------------------------------
