@@ -195,7 +195,7 @@ class ClockSampler:
         0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
