@@ -127,7 +127,10 @@ def make_inputs(kind: str, n: int, dtype: torch.dtype, batch: int, device, seed:
     return [a]
 
 
-def abi_launcher(lib, kind: str, n: int, code: int, batch: int, ins, out, stream: int):
+ALGOS = {"auto": 0, "ldl": 1, "lu": 2, "warp": 3}
+
+
+def abi_launcher(lib, kind: str, n: int, code: int, batch: int, ins, out, stream: int, algo: int = 0):
     """Zero-argument callable = one pass of the hot path through the C ABI
     (include/nfm.h), with every argument evaluated once up front."""
     import functools
@@ -135,11 +138,11 @@ def abi_launcher(lib, kind: str, n: int, code: int, batch: int, ins, out, stream
     p = [t.data_ptr() for t in ins]
     o = out.data_ptr()
     if kind == "sym_solve":
-        return functools.partial(lib.nfm_sym_solve, code, n, 2, 0, batch, p[0], lens[0], p[1], lens[1], None, 0, o, olen, stream)
+        return functools.partial(lib.nfm_sym_solve, code, n, 2, algo, batch, p[0], lens[0], p[1], lens[1], None, 0, o, olen, stream)
     if kind == "sym_matvec":
         return functools.partial(lib.nfm_sym_matvec, code, n, 2, batch, p[0], lens[0], p[1], lens[1], None, 0, 0, o, olen, stream)
     if kind == "sym_invert":
-        return functools.partial(lib.nfm_sym_invert, code, n, 0, 0, batch, p[0], lens[0], o, olen, stream)
+        return functools.partial(lib.nfm_sym_invert, code, n, algo, 0, batch, p[0], lens[0], o, olen, stream)
     if kind == "batch_inv":
         return functools.partial(lib.nfm_batch_inv, code, n, 0, 1, batch, p[0], lens[0], o, olen, stream)
     if kind == "batch_det":
@@ -281,6 +284,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sym_solve3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override the workload's batch (debug)")
+    ap.add_argument("--method", default="auto", choices=sorted(ALGOS), help="factorisation for sym_solve / sym_invert, N > 4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
@@ -300,7 +304,7 @@ def main():
     esize = 4 if dtype == torch.float32 else 8
     batch = args.batch or w["batch"]
     alg = algorithmic_bytes(kind, n, esize)
-    config = {"workload": w["desc"], "routine": kind, "n": n, "batch": batch, "bytes_per_matrix": alg}
+    config = {"workload": w["desc"], "routine": kind, "n": n, "batch": batch, "bytes_per_matrix": alg, "method": args.method}
 
     if args.impl == "reference":
         if rank != 0:
@@ -346,7 +350,7 @@ def main():
                     f"rotating {nsets} operand sets of {set_bytes / 2**20:.0f} MiB (> 3x L2 in total)")
 
     stream = torch.cuda.current_stream(dev).cuda_stream
-    launchers = [abi_launcher(lib, kind, n, code, my, ins, out, stream) for ins, out in sets]
+    launchers = [abi_launcher(lib, kind, n, code, my, ins, out, stream, ALGOS[args.method]) for ins, out in sets]
 
     def step(i):
         rc = launchers[i % nsets]()

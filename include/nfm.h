@@ -56,7 +56,7 @@ extern "C" {
 #define NFM_ALGO_AUTO 0 /* sym: closed form N<=4, LDL^T above; dense: closed form n<=3 (inverse/det), pivoted LU above */
 #define NFM_ALGO_LDL 1  /* LDL^T / Cholesky-type, no pivoting (SPD or strongly regular input) */
 #define NFM_ALGO_LU 2   /* LU with partial pivoting (any invertible input) */
-#define NFM_ALGO_WARP 3 /* sub-warp cooperative LDL^T with shuffles (N >= 5) */
+#define NFM_ALGO_WARP 3 /* sym_solve only: sub-warp cooperative elimination with shuffles (5 <= N <= 10), A/B variant */
 
 /* errors */
 #define NFM_OK 0
@@ -70,7 +70,8 @@ int nfm_version(void);
 const char *nfm_last_error_string(void);
 /* number of kernel launches issued by this library in the calling process */
 uint64_t nfm_launch_count(void);
-/* 1 if the last call on this thread used the TMA-staged fast path for its bulk */
+/* 1 if the last call on this thread used the TMA-staged thread-per-matrix fast
+ * path for its bulk, 2 if it used the sub-warp cooperative kernel, 0 otherwise */
 int nfm_last_path_was_tma(void);
 
 /* y = A v            (inp == NULL, sign ignored)

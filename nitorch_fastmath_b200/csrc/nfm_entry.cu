@@ -141,7 +141,8 @@ int nfm_sym_solve(int dtype, int n, int layout, int algo, int64_t batch, const v
   if (!big) return finish(dtype == NFM_F32 ? sym_solve_part0<float>(n, layout, a.p, s) : sym_solve_part0<double>(n, layout, a.p, s));
   if (algo == NFM_ALGO_LU)
     return finish(dtype == NFM_F32 ? sym_solve_part2<float>(n, a.p, s) : sym_solve_part2<double>(n, a.p, s));
-  if (algo == NFM_ALGO_WARP) return fail(NFM_E_UNSUPPORTED, "NFM_ALGO_WARP not built in this version");
+  if (algo == NFM_ALGO_WARP)
+    return finish(dtype == NFM_F32 ? sym_solve_warp<float>(n, a.p, s) : sym_solve_warp<double>(n, a.p, s));
   return finish(dtype == NFM_F32 ? sym_solve_part1<float>(n, a.p, s) : sym_solve_part1<double>(n, a.p, s));
 }
 
@@ -158,7 +159,7 @@ int nfm_sym_invert(int dtype, int n, int algo, int diag_only, int64_t batch, con
   auto s = static_cast<cudaStream_t>(stream);
   if (algo == NFM_ALGO_LU && n > 4)
     return finish(dtype == NFM_F32 ? sym_invert_part1<float>(n, diag_only, a.p, s) : sym_invert_part1<double>(n, diag_only, a.p, s));
-  if (algo == NFM_ALGO_WARP) return fail(NFM_E_UNSUPPORTED, "NFM_ALGO_WARP not built in this version");
+  // NFM_ALGO_WARP has no invert kernel: LDL^T thread-per-matrix
   return finish(dtype == NFM_F32 ? sym_invert_part0<float>(n, diag_only, a.p, s) : sym_invert_part0<double>(n, diag_only, a.p, s));
 }
 

@@ -16,6 +16,9 @@ template <typename T> int sym_solve_part0(int n, int layout, const KParams& p, c
 template <typename T> int sym_solve_part1(int n, const KParams& p, cudaStream_t s);
 template <typename T> int sym_solve_part2(int n, const KParams& p, cudaStream_t s);
 
+// NFM_ALGO_WARP: sub-warp cooperative shuffle solve, packed N 5..10 (nfm_sym_warp.cu)
+template <typename T> int sym_solve_warp(int n, const KParams& p, cudaStream_t s);
+
 // sym_invert: part 0 = N <= 4 closed form + N 5..10 LDL^T; part 1 = N 5..10 pivoted LU
 template <typename T> int sym_invert_part0(int n, int diag_only, const KParams& p, cudaStream_t s);
 template <typename T> int sym_invert_part1(int n, int diag_only, const KParams& p, cudaStream_t s);

@@ -56,6 +56,7 @@ def launch_list(path):
     text = text[text.index('"ID"'):]
     rows = list(csv.DictReader(io.StringIO(text)))
     agg = OrderedDict()
+    seq = []
     for r in rows:
         if r["Metric Name"] != "gpu__time_duration.sum":
             continue
@@ -66,6 +67,12 @@ def launch_list(path):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v
+        seq.append((name, v))
+    # the step region = everything after the last launch that is not ours
+    # (bench.py generates its synthetic input with torch first, then only
+    # launches libnfm kernels: warm-up steps + timed steps)
+    last_setup = max([i for i, (n, _) in enumerate(seq) if "nfm::" not in n], default=-1)
+    region = seq[last_setup + 1:]
     total = sum(a[1] for a in agg.values())
     print(f"# ncu --metrics gpu__time_duration.sum --clock-control none, source: {path}")
     print("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes")
@@ -73,6 +80,15 @@ def launch_list(path):
     print(f"{'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}  kernel")
     for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{cnt:8d} {us:12.1f} {us / cnt:10.2f} {us / total:7.1%}  {name[:150]}")
+    rt = sum(v for _, v in region)
+    print(f"\n# step region (warm-up + timed steps; after the last torch set-up launch): {len(region)} launches, {rt:.1f} us")
+    ragg = OrderedDict()
+    for n, v in region:
+        a = ragg.setdefault(n, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    for name, (cnt, us) in ragg.items():
+        print(f"{cnt:8d} {us:12.1f} {us / cnt:10.2f} {us / max(rt, 1e-9):7.1%}  {name[:150]}")
 
 
 if __name__ == "__main__":

@@ -116,6 +116,10 @@ def test_sym_fast_path_vs_oracle(nfm, dtype, n):
     close(nfm.sym_solve(dm, dv, 0.25), P.sym_solve(mat, vec, 0.25), dtype)
     close(nfm.sym_solve(dm, dv, [0.5, 0.25][:n]), P.sym_solve(mat, vec, [0.5, 0.25][:n]), dtype)
     close(nfm.sym_solve(dm, dv, method="lu"), P.sym_solve(mat, vec), dtype)
+    # the sub-warp cooperative shuffle variant (N >= 5; below it is the closed form)
+    close(nfm.sym_solve(dm, dv, method="warp"), P.sym_solve(mat, vec), dtype)
+    assert _lib.load().nfm_last_path_was_tma() == (2 if n >= 5 else 1)
+    close(nfm.sym_solve(dm, dv, dr, method="warp"), P.sym_solve(mat, vec, reg), dtype)
     close(nfm.sym_matvec(dm, dv), P.sym_matvec(mat, vec), dtype)
     terms = (inp, P.sym_matvec(mat, vec))
     close_sum(nfm.sym_addmatvec(di, dm, dv), P.sym_addmatvec(inp, mat, vec), terms, dtype)
