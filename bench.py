@@ -284,6 +284,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sym_solve3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="override the workload's batch (debug)")
+    ap.add_argument("--kind", default=None, help="custom workload: sym_solve|sym_matvec|sym_invert|batch_inv|batch_det|batch_solve")
+    ap.add_argument("--n", type=int, default=None, help="custom workload: matrix order")
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"], help="custom workload: scalar type")
     ap.add_argument("--method", default="auto", choices=sorted(ALGOS), help="factorisation for sym_solve / sym_invert, N > 4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -298,7 +301,13 @@ def main():
     if world != args.gpus and world != 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.kind or args.n or args.dtype:
+        w["kind"] = args.kind or w["kind"]
+        w["n"] = args.n or w["n"]
+        w["dtype"] = args.dtype or w["dtype"]
+        w["batch"] = args.batch or w["batch"]
+        w["desc"] = "custom: %s n=%d %s batch=%d" % (w["kind"], w["n"], w["dtype"], w["batch"])
     kind, n = w["kind"], w["n"]
     dtype = torch.float32 if w["dtype"] == "f32" else torch.float64
     esize = 4 if dtype == torch.float32 else 8

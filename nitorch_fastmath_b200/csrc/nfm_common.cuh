@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/nfm.h"
 
 namespace nfm {
@@ -104,6 +106,26 @@ __device__ __forceinline__ void bulk_wait() {
 // generic-proxy smem writes -> visible to the async proxy (before a bulk store)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Compile-time loop: f(std::integral_constant<int, i>) for i in [B, E).  The
+// factorisation kernels index register arrays with these constants, so the
+// arrays stay in registers no matter what the unroller's size heuristics say
+// (`#pragma unroll` alone left the order >= 6 pivoted kernels in local memory).
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+// descending: i = E-1 ... B
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for_down(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, E - 1>{});
+    static_for_down<B, E - 1>(f);
+  }
 }
 
 // programmatic dependent launch (PDL)

@@ -53,22 +53,24 @@ __device__ __forceinline__ void dense_inv_closed(const T (&a)[N * N], bool regul
   } else if constexpr (N == 2) {
     T dt = dense_det2(a);
     if (regularise) dt += abs_range(a) * T(1e-12);
-    f[0] = a[3] / dt;
-    f[1] = -a[1] / dt;
-    f[2] = -a[2] / dt;
-    f[3] = a[0] / dt;
+    const T r = T(1) / dt;  // one division; the reference divides every cofactor (<= 1 ulp apart)
+    f[0] = a[3] * r;
+    f[1] = -a[1] * r;
+    f[2] = -a[2] * r;
+    f[3] = a[0] * r;
   } else {
     T dt = dense_det3(a);
     if (regularise) dt += abs_range(a) * T(1e-12);
-    f[0] = (a[4] * a[8] - a[5] * a[7]) / dt;
-    f[1] = (a[2] * a[7] - a[1] * a[8]) / dt;
-    f[2] = (a[1] * a[5] - a[2] * a[4]) / dt;
-    f[3] = (a[5] * a[6] - a[3] * a[8]) / dt;
-    f[4] = (a[0] * a[8] - a[2] * a[6]) / dt;
-    f[5] = (a[3] * a[2] - a[5] * a[0]) / dt;
-    f[6] = (a[7] * a[3] - a[6] * a[4]) / dt;
-    f[7] = (a[6] * a[1] - a[7] * a[0]) / dt;
-    f[8] = (a[0] * a[4] - a[1] * a[3]) / dt;
+    const T r = T(1) / dt;
+    f[0] = (a[4] * a[8] - a[5] * a[7]) * r;
+    f[1] = (a[2] * a[7] - a[1] * a[8]) * r;
+    f[2] = (a[1] * a[5] - a[2] * a[4]) * r;
+    f[3] = (a[5] * a[6] - a[3] * a[8]) * r;
+    f[4] = (a[0] * a[8] - a[2] * a[6]) * r;
+    f[5] = (a[3] * a[2] - a[5] * a[0]) * r;
+    f[6] = (a[7] * a[3] - a[6] * a[4]) * r;
+    f[7] = (a[6] * a[1] - a[7] * a[0]) * r;
+    f[8] = (a[0] * a[4] - a[1] * a[3]) * r;
   }
 }
 
@@ -79,56 +81,58 @@ struct GaussJordan {
 
   __device__ __forceinline__ void invert() {
     int piv[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K;
       T best = tabs(a[k][k]);
       int p = k;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
         const T c = tabs(a[i][k]);
         if (c > best) {
           best = c;
           p = i;
         }
-      }
+      });
       piv[k] = p;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
         const bool sw = (p == i);
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
+        static_for<0, N>([&](auto J) {
+          constexpr int j = J;
           const T lo = a[k][j], hi = a[i][j];
           a[k][j] = sw ? hi : lo;
           a[i][j] = sw ? lo : hi;
-        }
-      }
+        });
+      });
       const T rp = T(1) / a[k][k];
       a[k][k] = T(1);
-#pragma unroll
-      for (int j = 0; j < N; ++j) a[k][j] *= rp;
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        if (i == k) continue;
-        const T f = a[i][k];
-        a[i][k] = T(0);
-#pragma unroll
-        for (int j = 0; j < N; ++j) a[i][j] -= f * a[k][j];
-      }
-    }
+      static_for<0, N>([&](auto J) { a[k][J] *= rp; });
+      static_for<0, N>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (i != k) {
+          const T f = a[i][k];
+          a[i][k] = T(0);
+          static_for<0, N>([&](auto J) {
+            constexpr int j = J;
+            a[i][j] -= f * a[k][j];
+          });
+        }
+      });
+    });
     // (P A)^-1 = A^-1 P^T  ->  undo with column swaps in reverse order
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-#pragma unroll
-      for (int c = k + 1; c < N; ++c) {
+    static_for_down<0, N>([&](auto K) {
+      constexpr int k = K;
+      static_for<k + 1, N>([&](auto C) {
+        constexpr int c = C;
         const bool sw = (piv[k] == c);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
+        static_for<0, N>([&](auto I) {
+          constexpr int i = I;
           const T lo = a[i][k], hi = a[i][c];
           a[i][k] = sw ? hi : lo;
           a[i][c] = sw ? lo : hi;
-        }
-      }
-    }
+        });
+      });
+    });
   }
 };
 

@@ -28,6 +28,7 @@ struct BatchInvOp {
   static constexpr int kLen2 = 1;
   static constexpr int kUse = 1;
   static constexpr int kOut = N * N;
+  static constexpr bool kHeavy = ALGO != NFM_ALGO_LDL && N >= 4;
 
   __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&)[1], const T (&)[1], int present,
                                                int flags, T (&out)[kOut]) {
@@ -66,6 +67,7 @@ struct BatchDetOp {
   static constexpr int kLen2 = 1;
   static constexpr int kUse = 1;
   static constexpr int kOut = 1;
+  static constexpr bool kHeavy = N >= 4;
 
   __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&)[1], const T (&)[1], int present,
                                                int flags, T (&out)[1]) {
@@ -93,6 +95,7 @@ struct BatchSolveOp {
   static constexpr int kLen2 = 1;
   static constexpr int kUse = 3;
   static constexpr int kOut = N;
+  static constexpr bool kHeavy = ALGO != NFM_ALGO_LDL && N >= 2;
 
   __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&b)[N], const T (&)[1], int present,
                                                int flags, T (&x)[N]) {
@@ -125,6 +128,7 @@ struct BatchMatvecOp {
   static constexpr int kLen2 = 1;
   static constexpr int kUse = 3;
   static constexpr int kOut = N;
+  static constexpr bool kHeavy = false;
 
   __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&v)[N], const T (&)[1], int present,
                                                int flags, T (&y)[N]) {

@@ -12,6 +12,7 @@ template <typename T, int N>
 struct SymDetOp {
   using scalar = T;
   static constexpr int kLen0 = packed_len(N), kLen1 = 1, kLen2 = 1, kUse = 1, kOut = 1;
+  static constexpr bool kHeavy = N > 4;
   __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&)[1], const T (&)[1], int, int, T (&out)[1]) {
     if constexpr (N <= 4) {
       out[0] = sym_det_closed<T, N>(m);
@@ -32,6 +33,7 @@ template <typename T, int N>
 struct SymToFullOp {
   using scalar = T;
   static constexpr int kLen0 = packed_len(N), kLen1 = 1, kLen2 = 1, kUse = 1, kOut = N * N;
+  static constexpr bool kHeavy = false;
   __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&)[1], const T (&)[1], int, int, T (&out)[kOut]) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -45,6 +47,7 @@ template <typename T, int N>
 struct SymOuterOp {
   using scalar = T;
   static constexpr int kLen0 = N, kLen1 = 1, kLen2 = 1, kUse = 1, kOut = packed_len(N);
+  static constexpr bool kHeavy = false;
   __device__ static __forceinline__ void apply(const T (&x)[N], const T (&)[1], const T (&)[1], int, int, T (&out)[kOut]) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -60,6 +63,7 @@ struct SymMatmulOp {
   static constexpr int kHN = MODE == 0 ? K : D;   // order of H
   static constexpr int kON = MODE == 0 ? D : K;   // order of the result
   static constexpr int kLen0 = K * D, kLen1 = packed_len(kHN), kLen2 = 1, kUse = 3, kOut = packed_len(kON);
+  static constexpr bool kHeavy = false;
   __device__ static __forceinline__ void apply(const T (&j)[kLen0], const T (&h)[kLen1], const T (&)[1], int, int, T (&out)[kOut]) {
     // G = J as (kON x kHN) "rows = output index": mode 0 uses J^T, mode 1 uses J
     T hj[kHN][kON];  // H * G^T

@@ -33,6 +33,7 @@
 //     static constexpr int kLen0, kLen1, kLen2;   // input record lengths (1 if unused)
 //     static constexpr int kUse;                   // bit mask of inputs the op can take
 //     static constexpr int kOut;                   // output record length
+//     static constexpr bool kHeavy;                // pivoted / long dependent chains (tile geometry hint)
 //     __device__ static void apply(const T(&)[kLen0], const T(&)[kLen1], const T(&)[kLen2],
 //                                  int present, int flags, T(&out)[kOut]);
 // Absent optional inputs arrive zero-filled.
@@ -301,7 +302,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // best configurations keep ONE large CTA per SM with 2 (big records) or 3
 // stages and ~130-150 KB of shared memory -- large bulk copies beat many small
 // ones -- so the rule is: stages = 2 when a matrix moves >= 100 B, else 3;
-// TILE = the largest of {64,128,256,384,512,768,1024} whose ring (mandatory
+// TILE = the largest of {64,...,1024} (2048 / 4096 for records of a few bytes) whose ring (mandatory
 // operands) + double-buffered output fits 152 KB; THREADS = 512 / 384 / 256 /
 // TILE.  Optional operands (regulariser, addend) grow the ring up to the
 // 227 KB limit.  TuneFixed pins ops whose measured optimum differs.
@@ -327,13 +328,23 @@ constexpr int kSmemTarget = 152 * 1024;
 
 constexpr int pick_tile(int stages, int in_bytes, int out_bytes) {
   const int per_matrix = stages * in_bytes + 2 * out_bytes;
-  const int cands[7] = {1024, 768, 512, 384, 256, 128, 64};
-  for (int i = 0; i < 7; ++i)
+  const int cands[9] = {4096, 2048, 1024, 768, 512, 384, 256, 128, 64};
+  for (int i = (per_matrix <= 48 ? 0 : per_matrix <= 96 ? 1 : 2); i < 9; ++i)
     if (cands[i] * per_matrix <= kSmemTarget) return cands[i];
   return 64;
 }
 
-constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile == 512 ? 256 : tile; }
+constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile == 512 ? 256 : tile; }  // MPT <= 8
+
+// Compute-heavy ops (pivoted elimination, Gauss-Jordan: Op::kHeavy) are bound by
+// the latency of their dependent chains rather than by HBM alone; they do best
+// with SEVERAL small CTAs per SM whose barrier phases interleave: 128 threads,
+// one matrix each, 3 stages (2 when the ring would pass 72 KB), tile 64 when
+// even that passes 100 KB  (profiles/r1_tile_geometry_sweep.txt, sweep 3).
+constexpr int heavy_stages(int in_bytes, int out_bytes) { return 128 * (3 * in_bytes + 2 * out_bytes) <= 72 * 1024 ? 3 : 2; }
+constexpr int heavy_tile(int in_bytes, int out_bytes) {
+  return 128 * (heavy_stages(in_bytes, out_bytes) * in_bytes + 2 * out_bytes) <= 100 * 1024 ? 128 : 64;
+}
 
 template <class Op>
 struct TuneRule : TuneBase<Op> {
@@ -341,17 +352,17 @@ struct TuneRule : TuneBase<Op> {
 #ifdef NFM_TUNE_STAGES
   static constexpr int kStages = NFM_TUNE_STAGES;
 #else
-  static constexpr int kStages = (B::kInBytes + B::kOutBytes >= 100) ? 2 : 3;
+  static constexpr int kStages = Op::kHeavy ? heavy_stages(B::kInBytes, B::kOutBytes) : (B::kInBytes + B::kOutBytes >= 100) ? 2 : 3;
 #endif
 #ifdef NFM_TUNE_TILE
   static constexpr int kTile = NFM_TUNE_TILE;
 #else
-  static constexpr int kTile = pick_tile(kStages, B::kInBytes, B::kOutBytes);
+  static constexpr int kTile = Op::kHeavy ? heavy_tile(B::kInBytes, B::kOutBytes) : pick_tile(kStages, B::kInBytes, B::kOutBytes);
 #endif
 #ifdef NFM_TUNE_THREADS
   static constexpr int kThreads = NFM_TUNE_THREADS < kTile ? NFM_TUNE_THREADS : kTile;
 #else
-  static constexpr int kThreads = pick_threads(kTile);
+  static constexpr int kThreads = Op::kHeavy ? kTile : pick_threads(kTile);
 #endif
   static constexpr int kMpt = kTile / kThreads;
 };

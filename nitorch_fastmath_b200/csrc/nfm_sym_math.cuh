@@ -43,13 +43,14 @@ __device__ __forceinline__ void sym_matvec_reg(const T (&a)[packed_len(N)], cons
         if (j != i) y[i] += a[pidx(N, i, j)] * v[j];
   } else {
     // generic variant walks the strict upper triangle row by row (:123-131)
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = i + 1; j < N; ++j) {
+    static_for<0, N>([&](auto I) {
+      constexpr int i = I;
+      static_for<i + 1, N>([&](auto J) {
+        constexpr int j = J;
         y[i] += a[pidx(N, i, j)] * v[j];
         y[j] += a[pidx(N, i, j)] * v[i];
-      }
+      });
+    });
   }
 }
 
@@ -100,19 +101,26 @@ __device__ __forceinline__ T sym_adjugate(const T (&m)[packed_len(N)], T (&adj)[
     adj[5] = u[0] * u[1] - d[0] * u[2];
     return sym_det3(d, u);
   } else {
-    // _impl/sym.py:253-322
+    // Same adjugate / determinant as _impl/sym.py:229-322, evaluated through the
+    // twelve 2x2 minors of rows (0,1) and (2,3) (Laplace expansion by
+    // complementary minors): ~100 flops instead of the ~250 of the expanded
+    // polynomials, which would make the 4x4 case issue-bound on B200.
     const T a = u[0], b = u[1], c = u[2], e = u[3], f = u[4], g = u[5];
-    adj[0] = d[1] * d[2] * d[3] - d[1] * sq(g) - d[2] * sq(f) - d[3] * sq(e) + T(2) * e * f * g;
-    adj[1] = d[0] * d[2] * d[3] - d[0] * sq(g) - d[2] * sq(c) - d[3] * sq(b) + T(2) * b * c * g;
-    adj[2] = d[0] * d[1] * d[3] - d[0] * sq(f) - d[1] * sq(c) - d[3] * sq(a) + T(2) * a * c * f;
-    adj[3] = d[0] * d[1] * d[2] - d[0] * sq(e) - d[1] * sq(b) - d[2] * sq(a) + T(2) * a * b * e;
-    adj[4] = -d[2] * d[3] * a + d[2] * c * f + d[3] * b * e + a * sq(g) - b * f * g - c * e * g;  // 01
-    adj[5] = -d[1] * d[3] * b + d[1] * c * g + d[3] * a * e + b * sq(f) - a * f * g - c * e * f;  // 02
-    adj[6] = -d[1] * d[2] * c + d[1] * b * g + d[2] * a * f + c * sq(e) - a * e * g - b * e * f;  // 03
-    adj[7] = -d[0] * d[3] * e + d[0] * f * g + d[3] * a * b + e * sq(c) - a * c * g - b * c * f;  // 12
-    adj[8] = -d[0] * d[2] * f + d[0] * e * g + d[2] * a * c + f * sq(b) - a * b * g - b * c * e;  // 13
-    adj[9] = -d[0] * d[1] * g + d[0] * f * e + d[1] * b * c + g * sq(a) - a * b * f - a * c * e;  // 23
-    return sym_det4(d, u);
+    const T s0 = d[0] * d[1] - a * a, s1 = d[0] * e - a * b, s2 = d[0] * f - a * c;
+    const T s3 = a * e - d[1] * b, s4 = a * f - d[1] * c, s5 = b * f - e * c;
+    const T c5 = d[2] * d[3] - g * g, c4 = e * d[3] - f * g, c3 = e * g - f * d[2];
+    const T c2 = b * d[3] - c * g, c1 = b * g - c * d[2], c0 = s5;
+    adj[0] = d[1] * c5 - e * c4 + f * c3;     // 00
+    adj[1] = d[0] * c5 - b * c2 + c * c1;     // 11
+    adj[2] = c * s4 - f * s2 + d[3] * s0;     // 22
+    adj[3] = b * s3 - e * s1 + d[2] * s0;     // 33
+    adj[4] = -a * c5 + b * c4 - c * c3;       // 01
+    adj[5] = f * s5 - g * s4 + d[3] * s3;     // 02
+    adj[6] = -e * s5 + d[2] * s4 - g * s3;    // 03
+    adj[7] = -c * s5 + g * s2 - d[3] * s1;    // 12
+    adj[8] = b * s5 - d[2] * s2 + g * s1;     // 13
+    adj[9] = -b * s4 + e * s2 - g * s0;       // 23
+    return s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
   }
 }
 
@@ -132,15 +140,18 @@ __device__ __forceinline__ void sym_solve_closed(const T (&m)[packed_len(N)], co
   } else {
     T adj[packed_len(N)];
     const T det = sym_adjugate<T, N>(m, adj);
-    if constexpr (N == 4) {
-      // reference accumulates diagonal term first, then the others in column order (:291-322)
+    if constexpr (N == 4 || sizeof(T) == 8) {
+      // reference accumulates diagonal term first, then the others in column
+      // order (:291-322) and divides every entry; one reciprocal here (<= 1 ulp
+      // apart): N = 4 and fp64 would otherwise be issue-bound on divisions
+      const T rdet = T(1) / det;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         T s = adj[i] * v[i];
 #pragma unroll
         for (int j = 0; j < N; ++j)
           if (j != i) s += adj[pidx(N, i, j)] * v[j];
-        x[i] = s / det;
+        x[i] = s * rdet;
       }
     } else {
 #pragma unroll
@@ -246,70 +257,73 @@ struct GaussPP {
   // diagonal, *not* normalised) and b is transformed accordingly
   __device__ __forceinline__ void eliminate() {
     det_sign = T(1);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      {
-        // pivot search: first row of maximal |a_ik|, i >= k  (LAPACK getrf / idamax)
-        T best = tabs(a[k][k]);
-        int p = k;
-#pragma unroll
-        for (int i = k + 1; i < N; ++i) {
-          const T c = tabs(a[i][k]);
-          if (c > best) {
-            best = c;
-            p = i;
-          }
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K;
+      // pivot search: first row of maximal |a_ik|, i >= k  (LAPACK getrf / idamax)
+      T best = tabs(a[k][k]);
+      int p = k;
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
+        const T c = tabs(a[i][k]);
+        if (c > best) {
+          best = c;
+          p = i;
         }
-#pragma unroll
-        for (int i = k + 1; i < N; ++i) {
-          const bool sw = (p == i);
-#pragma unroll
-          for (int j = k; j < N; ++j) {
-            const T lo = a[k][j], hi = a[i][j];
-            a[k][j] = sw ? hi : lo;
-            a[i][j] = sw ? lo : hi;
-          }
-#pragma unroll
-          for (int c = 0; c < R; ++c) {
-            const T lo = b[k][c], hi = b[i][c];
-            b[k][c] = sw ? hi : lo;
-            b[i][c] = sw ? lo : hi;
-          }
-        }
-        if (p != k) det_sign = -det_sign;
-      }
+      });
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
+        const bool sw = (p == i);
+        static_for<k, N>([&](auto J) {
+          constexpr int j = J;
+          const T lo = a[k][j], hi = a[i][j];
+          a[k][j] = sw ? hi : lo;
+          a[i][j] = sw ? lo : hi;
+        });
+        static_for<0, R>([&](auto C) {
+          constexpr int c = C;
+          const T lo = b[k][c], hi = b[i][c];
+          b[k][c] = sw ? hi : lo;
+          b[i][c] = sw ? lo : hi;
+        });
+      });
+      if (p != k) det_sign = -det_sign;
       const T rp = T(1) / a[k][k];
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
         const T f = a[i][k] * rp;
-#pragma unroll
-        for (int j = k + 1; j < N; ++j) a[i][j] -= f * a[k][j];
-#pragma unroll
-        for (int c = 0; c < R; ++c) b[i][c] -= f * b[k][c];
-      }
-    }
+        static_for<k + 1, N>([&](auto J) {
+          constexpr int j = J;
+          a[i][j] -= f * a[k][j];
+        });
+        static_for<0, R>([&](auto C) {
+          constexpr int c = C;
+          b[i][c] -= f * b[k][c];
+        });
+      });
+    });
   }
 
   __device__ __forceinline__ T det() const {
     T d = det_sign;
-#pragma unroll
-    for (int k = 0; k < N; ++k) d *= a[k][k];
+    static_for<0, N>([&](auto K) { d *= a[K][K]; });
     return d;
   }
 
   // back substitution: b <- U^-1 b
   __device__ __forceinline__ void back_substitute() {
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
+    static_for_down<0, N>([&](auto K) {
+      constexpr int k = K;
       const T rp = T(1) / a[k][k];
-#pragma unroll
-      for (int c = 0; c < R; ++c) {
+      static_for<0, R>([&](auto C) {
+        constexpr int c = C;
         T s = b[k][c];
-#pragma unroll
-        for (int j = k + 1; j < N; ++j) s -= a[k][j] * b[j][c];
+        static_for<k + 1, N>([&](auto J) {
+          constexpr int j = J;
+          s -= a[k][j] * b[j][c];
+        });
         b[k][c] = s * rp;
-      }
-    }
+      });
+    });
   }
 };
 

@@ -26,6 +26,7 @@ struct SymMatvecOp {
   static constexpr int kLen2 = N;
   static constexpr int kUse = 7;
   static constexpr int kOut = N;
+  static constexpr bool kHeavy = false;
 
   __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&v)[N], const T (&inp)[N], int present,
                                                int flags, T (&out)[N]) {
@@ -61,6 +62,7 @@ struct SymSolveOp {
   static constexpr int kLen2 = N;
   static constexpr int kUse = 7;
   static constexpr int kOut = N;
+  static constexpr bool kHeavy = (LAYOUT == NFM_LAYOUT_SYM && N > 4 && ALGO == NFM_ALGO_LU) || (LAYOUT == NFM_LAYOUT_FULL && N >= 2);
 
   __device__ static __forceinline__ void apply(const T (&m_in)[kLen0], const T (&v)[N], const T (&reg)[N],
                                                int present, int flags, T (&x)[N]) {
@@ -109,6 +111,7 @@ struct SymInvertOp {
   static constexpr int kLen2 = 1;
   static constexpr int kUse = 1;
   static constexpr int kOut = DIAG_ONLY ? N : packed_len(N);
+  static constexpr bool kHeavy = N > 4 && ALGO == NFM_ALGO_LU;
 
   __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&)[1], const T (&)[1], int present,
                                                int flags, T (&out)[kOut]) {
@@ -116,8 +119,14 @@ struct SymInvertOp {
       // reference: N solves against unit vectors = adjugate columns / det
       T adj[kLen0];
       const T det = sym_adjugate<T, N>(m, adj);
+      if constexpr (N == 4 || sizeof(T) == 8) {
+        const T rdet = T(1) / det;
 #pragma unroll
-      for (int k = 0; k < kOut; ++k) out[k] = adj[k] / det;
+        for (int k = 0; k < kOut; ++k) out[k] = adj[k] * rdet;
+      } else {
+#pragma unroll
+        for (int k = 0; k < kOut; ++k) out[k] = adj[k] / det;
+      }
     } else if constexpr (ALGO == NFM_ALGO_LU) {
       // in-place Gauss-Jordan with partial pivoting on the expanded matrix
       GaussJordan<T, N> g;
