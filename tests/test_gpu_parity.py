@@ -172,6 +172,56 @@ def test_ragged_tile_boundaries(nfm, batch):
     close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), torch.float64)
 
 
+@pytest.mark.parametrize("batch", [1, 77, 1024, 1030, 5000])
+def test_writes_stay_inside_the_output(nfm, batch):
+    """compute-sanitizer is not available on the GPU pool, so bounds are checked
+    with canaries: outputs live inside a larger buffer whose guard zones must be
+    untouched, and inputs must come back bit-identical (TMA bulk stores, the
+    segmented layout and the ragged-tail copy all write through raw pointers)."""
+    guard = 4096
+    sentinel = 12345.0
+
+    def guarded(shape, dtype):
+        numel = 1
+        for d in shape:
+            numel *= d
+        buf = torch.full((numel + 2 * guard,), sentinel, device=DEV, dtype=dtype)
+        return buf, buf[guard:guard + numel].view(shape)
+
+    def intact(buf, numel):
+        return bool((buf[:guard] == sentinel).all()) and bool((buf[guard + numel:] == sentinel).all())
+
+    for dtype in DTYPES:
+        for n in (3, 4, 6, 10):
+            nn = n * (n + 1) // 2
+            mat = G.spd_packed(batch, n, dtype, seed=n).to(DEV)
+            vec = G.vectors(batch, n, dtype, seed=n + 1).to(DEV)
+            mat0, vec0 = mat.clone(), vec.clone()
+            for fn, shape, args in (
+                (nfm.sym_solve, (batch, n), (mat, vec)),
+                (nfm.sym_matvec, (batch, n), (mat, vec)),
+                (nfm.sym_invert, (batch, nn), (mat,)),
+            ):
+                buf, out = guarded(shape, dtype)
+                fn(*args, out=out)
+                torch.cuda.synchronize()
+                assert intact(buf, out.numel()), (fn.__name__, n, dtype)
+                assert not bool((out == sentinel).any())
+            if n > 4:
+                buf, out = guarded((batch, n), dtype)
+                nfm.sym_solve(mat, vec, out=out, method="warp")
+                torch.cuda.synchronize()
+                assert intact(buf, out.numel())
+            assert torch.equal(mat, mat0) and torch.equal(vec, vec0)
+        for n in (2, 4, 8):                       # segmented layout
+            a = G.dense_shifted(batch, n, dtype, seed=n).to(DEV)
+            b = G.vectors(batch, n, dtype, seed=n + 1).to(DEV)
+            buf, out = guarded((batch, n), dtype)
+            nfm.solvevec(a, b, out=out)
+            torch.cuda.synchronize()
+            assert intact(buf, out.numel()) and not bool((out == sentinel).any())
+
+
 def test_back_to_back_launches_are_ordered(nfm):
     """Kernels are launched with programmatic stream serialization (they may
     become resident while the previous one drains); a chain of dependent
