@@ -119,6 +119,12 @@ def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
         _lib.check(rc, "nfm_sym_matvec")
     if copy_back:
         res.copy_(o.tensor)
+    if out is None and dtype is None:
+        want = tensors[0].dtype
+        for t in tensors[1:]:
+            want = torch.promote_types(want, t.dtype)
+        if want != res.dtype and want.is_floating_point:   # half / bfloat16 inputs: computed in fp32, returned as promoted
+            res = res.to(want)
     return res
 
 
@@ -216,7 +222,7 @@ def sym_solve(mat: Tensor, vec: Tensor,
     mat, vec = torch.as_tensor(mat), torch.as_tensor(vec)
     dev = D.common_device(mat, vec)
     cdt = D.compute_dtype(mat, vec, dtype=dtype)
-    res_dtype = dtype if dtype is not None else (vec.dtype if vec.dtype in (torch.float32, torch.float64) else cdt)
+    res_dtype = dtype if dtype is not None else vec.dtype   # reference: result has vec's dtype (half types compute in fp32)
     n = vec.shape[-1]
     _check_n(n)
     layout = D.detect_layout(mat.shape[-1], n)
@@ -337,6 +343,8 @@ def sym_invert(mat: Tensor, diag: bool = False, dtype: Optional[torch.dtype] = N
         _lib.check(rc, "nfm_sym_invert")
     if copy_back:
         res.copy_(o.tensor)
+    if out is None and dtype is None and mat.dtype != res.dtype and mat.dtype.is_floating_point:
+        res = res.to(mat.dtype)
     return res
 
 

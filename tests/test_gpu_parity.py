@@ -304,6 +304,40 @@ def test_dtype_semantics(nfm):
     assert z.dtype == torch.float64
 
 
+def test_half_precision_inputs_follow_reference_dtypes(nfm):
+    """fp16 / bf16 are not required (SURVEY 8a) but run through the reference;
+    here they compute in fp32 and come back in the reference's result dtype."""
+    mat = G.spd_packed(500, 3, torch.float32, seed=1)
+    vec = G.vectors(500, 3, torch.float32, seed=2)
+    for half in (torch.float16, torch.bfloat16):
+        x = nfm.sym_solve(mat.to(DEV, half), vec.to(DEV, half))
+        assert x.dtype == half
+        want = P.sym_solve(mat.to(half).float(), vec.to(half).float())
+        assert G.rel_err(x.float(), want) < (2e-2 if half == torch.bfloat16 else 3e-3)
+        assert nfm.sym_matvec(mat.to(DEV, half), vec.to(DEV)).dtype == torch.float32
+        assert nfm.sym_invert(mat.to(DEV, half)).dtype == half
+
+
+def test_cuda_graph_capture(nfm):
+    """The C ABI neither allocates nor synchronises, so calls can be captured
+    in a CUDA graph and replayed (launch-bound loops)."""
+    mat = G.spd_packed(100_000, 3, torch.float32, seed=1)
+    vec = G.vectors(100_000, 3, torch.float32, seed=2)
+    dm, dv = mat.to(DEV), vec.to(DEV)
+    out = torch.empty_like(dv)
+    nfm.sym_solve(dm, dv, out=out)                      # warm (function attributes, occupancy)
+    torch.cuda.synchronize()
+    out.zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(4):
+            nfm.sym_solve(dm, dv, out=out)
+    assert float(out.abs().sum()) == 0.0                # captured, not run
+    graph.replay()
+    torch.cuda.synchronize()
+    close(out, P.sym_solve(mat, vec), torch.float32)
+
+
 @pytest.mark.parametrize("n", [3, 6])
 def test_inplace_variants(nfm, n):
     dtype = torch.float32
