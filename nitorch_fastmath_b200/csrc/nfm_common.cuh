@@ -75,13 +75,23 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 
 // 1-D TMA: global -> shared, completion counted in bytes on an mbarrier.
 // src, dst 16-byte aligned, bytes % 16 == 0.   SASS: UBLKCP
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
-                                         uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
+// kHint: tag the lines evict_first in L2.  Measured on B200 (profiles/
+// r1_tile_geometry_sweep.txt, "build:" blocks): the hint costs 3-8 % on
+// read-heavy ops (solve, matvec, det) and gains 2-5 % on ops that write as much
+// as they read (invert, inverse), so the caller decides.
+template <bool kHint>
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  if constexpr (kHint) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+  } else {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
 }
 
 // 1-D TMA: shared -> global, tracked by the bulk async-group of the issuing thread.

@@ -129,6 +129,8 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
   const int rem = int(p.batch - ntiles * TILE);
   const i64 ntiles_all = ntiles + (rem > 0 ? 1 : 0);
   constexpr int kIssuers = SEG ? kSegs : 1;  // threads that issue bulk copies (one segment each)
+  // L2 evict_first on the loads only for ops that write at least as much as they read
+  constexpr bool kHint = Op::kOut >= ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0);
 
   extern __shared__ __align__(128) unsigned char smem[];
   const int staged = staged_mask(p);
@@ -171,17 +173,17 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
     const int seg = SEG ? tid : 0;
     if (staged & 1) {
       constexpr int sb = G::kBytes0 / nseg;
-      bulk_g2s(dst + seg * (sb + (SEG ? kSegPad : 0)), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb,
+      bulk_g2s<kHint>(dst + seg * (sb + (SEG ? kSegPad : 0)), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb,
                sb, &full[stage], policy);
     }
     if (staged & 2) {
       constexpr int sb = G::kBytes1 / nseg;
-      bulk_g2s(dst + f0 + seg * (sb + (SEG ? kSegPad : 0)),
+      bulk_g2s<kHint>(dst + f0 + seg * (sb + (SEG ? kSegPad : 0)),
                reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb, sb, &full[stage], policy);
     }
     if (staged & 4) {
       constexpr int sb = G::kBytes2 / nseg;
-      bulk_g2s(dst + f0 + f1 + seg * (sb + (SEG ? kSegPad : 0)),
+      bulk_g2s<kHint>(dst + f0 + f1 + seg * (sb + (SEG ? kSegPad : 0)),
                reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb, sb, &full[stage], policy);
     }
   };

@@ -70,9 +70,9 @@ __global__ void __launch_bounds__(THREADS) warp_solve_kernel(const __grid_consta
     unsigned char* dst = in_base + stage * stage_bytes;
     const i64 first = tile * TILE;
     mbar_arrive_expect_tx(&full[stage], uint32_t(stage_bytes));
-    bulk_g2s(dst, gmat + first * NN, kBytesMat, &full[stage], policy);
-    bulk_g2s(dst + kBytesMat, gvec + first * N, kBytesVec, &full[stage], policy);
-    if (has_diag) bulk_g2s(dst + kBytesMat + kBytesVec, gdiag + first * N, kBytesVec, &full[stage], policy);
+    bulk_g2s<false>(dst, gmat + first * NN, kBytesMat, &full[stage], policy);
+    bulk_g2s<false>(dst + kBytesMat, gvec + first * N, kBytesVec, &full[stage], policy);
+    if (has_diag) bulk_g2s<false>(dst + kBytesMat + kBytesVec, gdiag + first * N, kBytesVec, &full[stage], policy);
   };
 
   if (tid == 0) {
