@@ -134,6 +134,32 @@ int nfm_batch_matvec(int dtype, int m, int n, int64_t batch,
                      const void *vec, int64_t vec_stride,
                      void *out, int64_t out_stride, void *stream);
 
+/* ---- general strides --------------------------------------------------
+ * The *_ex variants describe every operand with a batch stride AND the stride
+ * between the elements of one record, both in elements.  elem_stride == 1 is
+ * the contiguous record of the plain entry points (which are thin wrappers
+ * over these).  Any other value -- typically coefficient-FIRST storage
+ * (C, X, Y, Z) viewed coefficient-last, i.e. batch_stride 1 and elem_stride
+ * X*Y*Z, which is also what the reference's own sym_solve returns
+ * (_impl/sym.py:398) -- is read in place by the strided kernel: adjacent
+ * threads then touch adjacent addresses, so no copy to AoS is needed. */
+typedef struct nfm_operand {
+  const void *ptr;
+  int64_t batch_stride;
+  int64_t elem_stride;
+} nfm_operand;
+
+int nfm_sym_matvec_ex(int dtype, int n, int layout, int64_t batch,
+                      const nfm_operand *mat, const nfm_operand *vec,
+                      const nfm_operand *inp /* nullable */, int sign,
+                      const nfm_operand *out, void *stream);
+int nfm_sym_solve_ex(int dtype, int n, int layout, int algo, int64_t batch,
+                     const nfm_operand *mat, const nfm_operand *vec,
+                     const nfm_operand *diag /* nullable */,
+                     const nfm_operand *out, void *stream);
+int nfm_sym_invert_ex(int dtype, int n, int algo, int diag_only, int64_t batch,
+                      const nfm_operand *mat, const nfm_operand *out, void *stream);
+
 /* ---- "next" rows -------------------------------- */
 
 /* out[b] = det of a packed symmetric matrix.  Replaces sym_det _impl/sym.py:401-452. */

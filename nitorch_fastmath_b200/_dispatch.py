@@ -74,36 +74,50 @@ def _collapse(shape: Sequence[int], strides: Sequence[int]) -> Optional[int]:
 
 
 class Operand:
-    """(pointer, batch stride) view of a tensor; keeps the storage alive."""
-    __slots__ = ("tensor", "ptr", "stride")
+    """(pointer, batch stride, element stride) view of a tensor; keeps the storage alive."""
+    __slots__ = ("tensor", "ptr", "stride", "estride")
 
-    def __init__(self, tensor: torch.Tensor, stride: int):
+    def __init__(self, tensor: torch.Tensor, stride: int, estride: int = 1):
         self.tensor = tensor
         self.ptr = tensor.data_ptr()
         self.stride = stride
+        self.estride = estride
+
+    def c_struct(self) -> "_lib.NfmOperand":
+        return _lib.NfmOperand(self.ptr, self.stride, self.estride)
 
 
-def as_operand(t: torch.Tensor, batch_shape: Tuple[int, ...], rec_ndim: int, dtype: torch.dtype) -> Operand:
-    """Broadcast ``t``'s batch dims to ``batch_shape`` and express it as one stride."""
+def as_operand(t: torch.Tensor, batch_shape: Tuple[int, ...], rec_ndim: int, dtype: torch.dtype,
+               allow_estride: bool = False) -> Operand:
+    """Broadcast ``t``'s batch dims to ``batch_shape`` and express it as one
+    batch stride.  With ``allow_estride`` a 1-D record whose elements are not
+    adjacent (coefficient-first storage viewed coefficient-last) is passed as
+    is, with its element stride, instead of being copied."""
     if t.dtype != dtype:
         t = t.to(dtype)
     rec_shape = tuple(t.shape[t.dim() - rec_ndim:]) if rec_ndim else ()
     rec_len = math.prod(rec_shape)
-    if not _record_contiguous(t, rec_ndim):
-        t = t.contiguous()
-    full = t.expand(*batch_shape, *rec_shape)
+    estride = 1
     nb = len(batch_shape)
+    if not _record_contiguous(t, rec_ndim):
+        full = t.expand(*batch_shape, *rec_shape)
+        bstride = _collapse(full.shape[:nb], full.stride()[:nb])
+        if allow_estride and rec_ndim == 1 and t.stride(-1) > 0 and (bstride is None or bstride > 0):
+            estride = t.stride(-1)          # strided record, collapsible non-broadcast batch: no copy
+        else:
+            t = t.contiguous()
+    full = t.expand(*batch_shape, *rec_shape)
     stride = _collapse(full.shape[:nb], full.stride()[:nb])
     if stride is None:
-        stride = rec_len
+        stride = rec_len if estride == 1 else 0
     elif stride < 0:
         full = full.contiguous()
-        stride = rec_len
-    return Operand(full, stride)
+        stride, estride = rec_len, 1
+    return Operand(full, stride, estride)
 
 
 def out_operand(out: Optional[torch.Tensor], shape: Tuple[int, ...], rec_ndim: int, dtype: torch.dtype,
-                device: torch.device):
+                device: torch.device, allow_estride: bool = False):
     """Returns (operand to write into, tensor to return, needs_copy_back)."""
     if out is None:
         res = torch.empty(shape, dtype=dtype, device=device)
@@ -114,15 +128,21 @@ def out_operand(out: Optional[torch.Tensor], shape: Tuple[int, ...], rec_ndim: i
     if out.device != device:
         raise RuntimeError("out lives on a different device")
     nb = len(shape) - rec_ndim
-    ok = out.dtype == dtype and _record_contiguous(out, rec_ndim)
+    estride = 1
+    ok = out.dtype == dtype
+    if ok and not _record_contiguous(out, rec_ndim):
+        if allow_estride and rec_ndim == 1 and out.stride(-1) > 0:
+            estride = out.stride(-1)
+        else:
+            ok = False
     stride = _collapse(out.shape[:nb], out.stride()[:nb]) if ok else -1
     rec_len = math.prod(shape[nb:]) if rec_ndim else 1
     if stride is None:
-        stride = rec_len
+        stride = rec_len if estride == 1 else 0
     if not ok or stride < 0 or (stride == 0 and math.prod(shape[:nb]) > 1):
         tmp = torch.empty(shape, dtype=dtype, device=device)
         return Operand(tmp, rec_len), out, True
-    return Operand(out, stride), out, False
+    return Operand(out, stride, estride), out, False
 
 
 def batch_count(batch_shape: Sequence[int]) -> int:

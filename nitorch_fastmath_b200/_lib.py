@@ -20,6 +20,14 @@ MAX_N = 10
 
 _P, _I, _L = c_void_p, c_int, c_int64
 
+
+class NfmOperand(ctypes.Structure):
+    """``nfm_operand`` of include/nfm.h: pointer, batch stride, element stride (in elements)."""
+    _fields_ = [("ptr", c_void_p), ("batch_stride", c_int64), ("elem_stride", c_int64)]
+
+
+_O = ctypes.POINTER(NfmOperand)
+
 # name -> (restype, argtypes); mirrors include/nfm.h declaration by declaration
 SIGNATURES = {
     "nfm_version": (c_int, []),
@@ -29,6 +37,9 @@ SIGNATURES = {
     "nfm_sym_matvec": (c_int, [_I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P]),
     "nfm_sym_solve": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P]),
     "nfm_sym_invert": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P]),
+    "nfm_sym_matvec_ex": (c_int, [_I, _I, _I, _L, _O, _O, _O, _I, _O, _P]),
+    "nfm_sym_solve_ex": (c_int, [_I, _I, _I, _I, _L, _O, _O, _O, _O, _P]),
+    "nfm_sym_invert_ex": (c_int, [_I, _I, _I, _I, _L, _O, _O, _P]),
     "nfm_batch_inv": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P]),
     "nfm_batch_det": (c_int, [_I, _I, _L, _P, _L, _P, _L, _P]),
     "nfm_batch_solve": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P]),

@@ -13,11 +13,17 @@ namespace nfm {
 
 using i64 = long long;
 
-// One batched operand: base pointer + batch stride in elements (0 = broadcast).
+// One batched operand: base pointer, batch stride in elements (0 = broadcast)
+// and the stride between the elements of one record (0 is read as 1, the
+// contiguous record; anything else -- e.g. coefficient-first "SoA" storage
+// viewed coefficient-last -- takes the strided kernel).
 struct Operand {
   const void* ptr;
   i64 stride;
+  i64 estride;
 };
+
+__host__ __device__ inline i64 elem_stride(i64 estride) { return estride == 0 ? 1 : estride; }
 
 constexpr int kMaxIn = 3;
 
@@ -26,6 +32,7 @@ struct KParams {
   Operand in[kMaxIn];
   void* out;
   i64 out_stride;
+  i64 out_estride;
   i64 batch;     // matrices handled by this launch
   int present;   // bit i set: input operand i is present
   int flags;     // op-specific
@@ -197,15 +204,15 @@ __device__ __forceinline__ void store_record(T* __restrict__ dst, const T (&r)[L
 
 // element-wise movers for the strided kernel (no alignment assumption)
 template <typename T, int L>
-__device__ __forceinline__ void load_record_scalar(const T* src, T (&r)[L]) {
+__device__ __forceinline__ void load_record_scalar(const T* src, T (&r)[L], i64 es = 1) {
 #pragma unroll
-  for (int k = 0; k < L; ++k) r[k] = src[k];  // plain loads: src may alias the output (in-place ops)
+  for (int k = 0; k < L; ++k) r[k] = src[k * es];  // plain loads: src may alias the output (in-place ops)
 }
 
 template <typename T, int L>
-__device__ __forceinline__ void store_record_scalar(T* dst, const T (&r)[L]) {
+__device__ __forceinline__ void store_record_scalar(T* dst, const T (&r)[L], i64 es = 1) {
 #pragma unroll
-  for (int k = 0; k < L; ++k) dst[k] = r[k];
+  for (int k = 0; k < L; ++k) dst[k * es] = r[k];
 }
 
 template <typename T, int L>

@@ -52,21 +52,37 @@ int fail(int code, const char* what) {
 struct Args {
   KParams p{};
   int rc = NFM_OK;
-  void in(int slot, const void* ptr, i64 stride, bool required) {
+  void in(int slot, const void* ptr, i64 stride, bool required, i64 estride = 1) {
     if (ptr == nullptr) {
       if (required) rc = fail(NFM_E_BADARG, "required operand is NULL");
       return;
     }
-    if (stride < 0) rc = fail(NFM_E_BADARG, "negative batch stride");
+    if (stride < 0 || estride < 0) rc = fail(NFM_E_BADARG, "negative stride");
     p.in[slot].ptr = ptr;
     p.in[slot].stride = stride;
+    p.in[slot].estride = estride;
     p.present |= 1 << slot;
   }
-  void out(void* ptr, i64 stride) {
+  void in(int slot, const nfm_operand* op, bool required) {
+    if (op == nullptr) {
+      if (required) rc = fail(NFM_E_BADARG, "required operand is NULL");
+      return;
+    }
+    in(slot, op->ptr, op->batch_stride, required, op->elem_stride);
+  }
+  void out(void* ptr, i64 stride, i64 estride = 1) {
     if (ptr == nullptr) rc = fail(NFM_E_BADARG, "output is NULL");
-    if (stride < 0) rc = fail(NFM_E_BADARG, "negative batch stride");
+    if (stride < 0 || estride < 0) rc = fail(NFM_E_BADARG, "negative stride");
     p.out = ptr;
     p.out_stride = stride;
+    p.out_estride = estride;
+  }
+  void out(const nfm_operand* op) {
+    if (op == nullptr) {
+      rc = fail(NFM_E_BADARG, "output is NULL");
+      return;
+    }
+    out(const_cast<void*>(op->ptr), op->batch_stride, op->elem_stride);
   }
 };
 
@@ -103,37 +119,43 @@ const char* nfm_last_error_string(void) { return nfm::t_error; }
 uint64_t nfm_launch_count(void) { return g_launch_count.load(); }
 int nfm_last_path_was_tma(void) { return t_last_path_tma; }
 
-int nfm_sym_matvec(int dtype, int n, int layout, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,
-                   int64_t vec_stride, const void* inp, int64_t inp_stride, int sign, void* out, int64_t out_stride,
-                   void* stream) {
+int nfm_sym_matvec_ex(int dtype, int n, int layout, int64_t batch, const nfm_operand* mat, const nfm_operand* vec,
+                      const nfm_operand* inp, int sign, const nfm_operand* out, void* stream) {
   int rc = NFM_OK;
   if (!check_common(dtype, n, batch, rc)) return rc;
   if (layout < 0 || layout > 3) return fail(NFM_E_UNSUPPORTED, "unknown layout");
-  if (inp != nullptr && sign != 1 && sign != -1) return fail(NFM_E_BADARG, "sign must be +1 or -1 when inp is given");
+  const bool has_inp = inp != nullptr && inp->ptr != nullptr;
+  if (has_inp && sign != 1 && sign != -1) return fail(NFM_E_BADARG, "sign must be +1 or -1 when inp is given");
   Args a;
-  a.in(0, mat, mat_stride, true);
-  a.in(1, vec, vec_stride, true);
-  a.in(2, inp, inp_stride, false);
-  a.out(out, out_stride);
+  a.in(0, mat, true);
+  a.in(1, vec, true);
+  if (has_inp) a.in(2, inp, false);
+  a.out(out);
   if (a.rc) return a.rc;
   a.p.batch = batch;
-  a.p.flags = (inp != nullptr && sign < 0) ? 1 : 0;
+  a.p.flags = (has_inp && sign < 0) ? 1 : 0;
   auto s = static_cast<cudaStream_t>(stream);
   return finish(dtype == NFM_F32 ? sym_matvec_impl<float>(n, layout, a.p, s) : sym_matvec_impl<double>(n, layout, a.p, s));
 }
 
-int nfm_sym_solve(int dtype, int n, int layout, int algo, int64_t batch, const void* mat, int64_t mat_stride,
-                  const void* vec, int64_t vec_stride, const void* diag, int64_t diag_stride, void* out,
-                  int64_t out_stride, void* stream) {
+int nfm_sym_matvec(int dtype, int n, int layout, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,
+                   int64_t vec_stride, const void* inp, int64_t inp_stride, int sign, void* out, int64_t out_stride,
+                   void* stream) {
+  const nfm_operand m{mat, mat_stride, 1}, v{vec, vec_stride, 1}, i{inp, inp_stride, 1}, o{out, out_stride, 1};
+  return nfm_sym_matvec_ex(dtype, n, layout, batch, &m, &v, inp ? &i : nullptr, sign, &o, stream);
+}
+
+int nfm_sym_solve_ex(int dtype, int n, int layout, int algo, int64_t batch, const nfm_operand* mat, const nfm_operand* vec,
+                     const nfm_operand* diag, const nfm_operand* out, void* stream) {
   int rc = NFM_OK;
   if (!check_common(dtype, n, batch, rc)) return rc;
   if (layout < 0 || layout > 3) return fail(NFM_E_UNSUPPORTED, "unknown layout");
   if (algo < NFM_ALGO_AUTO || algo > NFM_ALGO_WARP) return fail(NFM_E_UNSUPPORTED, "unknown algo");
   Args a;
-  a.in(0, mat, mat_stride, true);
-  a.in(1, vec, vec_stride, true);
-  a.in(2, diag, diag_stride, false);
-  a.out(out, out_stride);
+  a.in(0, mat, true);
+  a.in(1, vec, true);
+  if (diag != nullptr && diag->ptr != nullptr) a.in(2, diag, false);
+  a.out(out);
   if (a.rc) return a.rc;
   a.p.batch = batch;
   auto s = static_cast<cudaStream_t>(stream);
@@ -146,14 +168,21 @@ int nfm_sym_solve(int dtype, int n, int layout, int algo, int64_t batch, const v
   return finish(dtype == NFM_F32 ? sym_solve_part1<float>(n, a.p, s) : sym_solve_part1<double>(n, a.p, s));
 }
 
-int nfm_sym_invert(int dtype, int n, int algo, int diag_only, int64_t batch, const void* mat, int64_t mat_stride,
-                   void* out, int64_t out_stride, void* stream) {
+int nfm_sym_solve(int dtype, int n, int layout, int algo, int64_t batch, const void* mat, int64_t mat_stride,
+                  const void* vec, int64_t vec_stride, const void* diag, int64_t diag_stride, void* out,
+                  int64_t out_stride, void* stream) {
+  const nfm_operand m{mat, mat_stride, 1}, v{vec, vec_stride, 1}, d{diag, diag_stride, 1}, o{out, out_stride, 1};
+  return nfm_sym_solve_ex(dtype, n, layout, algo, batch, &m, &v, diag ? &d : nullptr, &o, stream);
+}
+
+int nfm_sym_invert_ex(int dtype, int n, int algo, int diag_only, int64_t batch, const nfm_operand* mat,
+                      const nfm_operand* out, void* stream) {
   int rc = NFM_OK;
   if (!check_common(dtype, n, batch, rc)) return rc;
   if (algo < NFM_ALGO_AUTO || algo > NFM_ALGO_WARP) return fail(NFM_E_UNSUPPORTED, "unknown algo");
   Args a;
-  a.in(0, mat, mat_stride, true);
-  a.out(out, out_stride);
+  a.in(0, mat, true);
+  a.out(out);
   if (a.rc) return a.rc;
   a.p.batch = batch;
   auto s = static_cast<cudaStream_t>(stream);
@@ -161,6 +190,12 @@ int nfm_sym_invert(int dtype, int n, int algo, int diag_only, int64_t batch, con
     return finish(dtype == NFM_F32 ? sym_invert_part1<float>(n, diag_only, a.p, s) : sym_invert_part1<double>(n, diag_only, a.p, s));
   // NFM_ALGO_WARP has no invert kernel: LDL^T thread-per-matrix
   return finish(dtype == NFM_F32 ? sym_invert_part0<float>(n, diag_only, a.p, s) : sym_invert_part0<double>(n, diag_only, a.p, s));
+}
+
+int nfm_sym_invert(int dtype, int n, int algo, int diag_only, int64_t batch, const void* mat, int64_t mat_stride,
+                   void* out, int64_t out_stride, void* stream) {
+  const nfm_operand m{mat, mat_stride, 1}, o{out, out_stride, 1};
+  return nfm_sym_invert_ex(dtype, n, algo, diag_only, batch, &m, &o, stream);
 }
 
 int nfm_batch_inv(int dtype, int n, int algo, int closed_form_reg, int64_t batch, const void* mat, int64_t a_stride,

@@ -280,11 +280,11 @@ __global__ void __launch_bounds__(128) strided_kernel(const __grid_constant__ KP
     zero_record(r0);
     zero_record(r1);
     zero_record(r2);
-    if (p.present & 1) load_record_scalar(g0 + b * p.in[0].stride, r0);
-    if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1);
-    if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2);
+    if (p.present & 1) load_record_scalar(g0 + b * p.in[0].stride, r0, elem_stride(p.in[0].estride));
+    if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1, elem_stride(p.in[1].estride));
+    if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2, elem_stride(p.in[2].estride));
     Op::apply(r0, r1, r2, p.present, p.flags, o);
-    store_record_scalar(gout + b * p.out_stride, o);
+    store_record_scalar(gout + b * p.out_stride, o, elem_stride(p.out_estride));
   }
 }
 
@@ -464,10 +464,11 @@ int run_op(KParams p, cudaStream_t stream) {
   t_last_path_tma = 0;
   if (p.batch == 0) return NFM_OK;
   const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2};
-  bool fast = p.out_stride == Op::kOut && aligned16(p.out);
+  bool fast = p.out_stride == Op::kOut && elem_stride(p.out_estride) == 1 && aligned16(p.out);
   int nstaged = 0;
   for (int i = 0; i < kMaxIn && fast; ++i) {
     if (!((p.present >> i) & 1)) continue;
+    if (elem_stride(p.in[i].estride) != 1) fast = false;
     if (p.in[i].stride == 0) continue;  // broadcast
     if (p.in[i].stride != lens[i] || !aligned16(p.in[i].ptr)) fast = false;
     ++nstaged;

@@ -14,6 +14,9 @@ int sym_solve_warp(int n, const KParams& p0, cudaStream_t s) {
   bool ok = n >= 5 && n <= NFM_MAX_N && p.out_stride == n && aligned16(p.out) && p.in[0].stride == nn &&
             aligned16(p.in[0].ptr) && p.in[1].stride == n && aligned16(p.in[1].ptr);
   if ((p.present & 4) && (p.in[2].stride != n || !aligned16(p.in[2].ptr))) ok = false;
+  if (elem_stride(p.out_estride) != 1 || elem_stride(p.in[0].estride) != 1 || elem_stride(p.in[1].estride) != 1 ||
+      ((p.present & 4) && elem_stride(p.in[2].estride) != 1))
+    ok = false;
   i64 done = 0;
   if (ok) {
     int rc = 0;

@@ -106,16 +106,15 @@ def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
             return out
         return r.cpu()
 
-    o, res, copy_back = D.out_operand(out, (*batch, n), 1, cdt, dev)
+    o, res, copy_back = D.out_operand(out, (*batch, n), 1, cdt, dev, allow_estride=True)
     if nb > 0:
-        m = D.as_operand(mat, batch, 1, cdt)
-        v = D.as_operand(vec, batch, 1, cdt)
-        i = D.as_operand(inp, batch, 1, cdt) if inp is not None else None
+        m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
+        v = D.as_operand(vec, batch, 1, cdt, allow_estride=True)
+        i = D.as_operand(inp, batch, 1, cdt, allow_estride=True) if inp is not None else None
         with torch.cuda.device(dev):
-            rc = _lib.load().nfm_sym_matvec(
-                code, n, layout, nb, m.ptr, m.stride, v.ptr, v.stride,
-                i.ptr if i is not None else None, i.stride if i is not None else 0, sign,
-                o.ptr, o.stride, D.current_stream_ptr(dev))
+            rc = _lib.load().nfm_sym_matvec_ex(
+                code, n, layout, nb, m.c_struct(), v.c_struct(), i.c_struct() if i is not None else None, sign,
+                o.c_struct(), D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_sym_matvec")
     if copy_back:
         res.copy_(o.tensor)
@@ -257,16 +256,16 @@ def sym_solve(mat: Tensor, vec: Tensor,
             return out
         return r.cpu()
 
-    o, res, copy_back = D.out_operand(out if (out is None or out.dtype == cdt) else None, (*batch, n), 1, cdt, dev)
+    o, res, copy_back = D.out_operand(out if (out is None or out.dtype == cdt) else None, (*batch, n), 1, cdt, dev,
+                                      allow_estride=True)
     if nb > 0:
-        m = D.as_operand(mat, batch, 1, cdt)
-        v = D.as_operand(vec, batch, 1, cdt)
-        r = D.as_operand(reg, batch, 1, cdt) if reg is not None else None
+        m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
+        v = D.as_operand(vec, batch, 1, cdt, allow_estride=True)
+        r = D.as_operand(reg, batch, 1, cdt, allow_estride=True) if reg is not None else None
         with torch.cuda.device(dev):
-            rc = _lib.load().nfm_sym_solve(
-                code, n, layout, algo, nb, m.ptr, m.stride, v.ptr, v.stride,
-                r.ptr if r is not None else None, r.stride if r is not None else 0,
-                o.ptr, o.stride, D.current_stream_ptr(dev))
+            rc = _lib.load().nfm_sym_solve_ex(
+                code, n, layout, algo, nb, m.c_struct(), v.c_struct(), r.c_struct() if r is not None else None,
+                o.c_struct(), D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_sym_solve")
     if copy_back:
         res.copy_(o.tensor)
@@ -334,12 +333,12 @@ def sym_invert(mat: Tensor, diag: bool = False, dtype: Optional[torch.dtype] = N
             return out
         return r.cpu()
 
-    o, res, copy_back = D.out_operand(out, (*batch, no), 1, cdt, dev)
+    o, res, copy_back = D.out_operand(out, (*batch, no), 1, cdt, dev, allow_estride=True)
     if nb > 0:
-        m = D.as_operand(mat, batch, 1, cdt)
+        m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
         with torch.cuda.device(dev):
-            rc = _lib.load().nfm_sym_invert(code, n, algo, int(bool(diag)), nb, m.ptr, m.stride, o.ptr, o.stride,
-                                            D.current_stream_ptr(dev))
+            rc = _lib.load().nfm_sym_invert_ex(code, n, algo, int(bool(diag)), nb, m.c_struct(), o.c_struct(),
+                                               D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_sym_invert")
     if copy_back:
         res.copy_(o.tensor)

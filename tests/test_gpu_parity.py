@@ -291,6 +291,35 @@ def test_strided_and_unaligned(nfm, n):
     close(nfm.sym_invert(cf), P.sym_invert(mat.reshape(-1, nn)), dtype)
 
 
+@pytest.mark.parametrize("n", [3, 6])
+def test_coefficient_first_fields_are_read_in_place(nfm, n):
+    """Channel-first fields (C, X, Y, Z) viewed coefficient-last -- what nitorch
+    keeps and what the reference's own sym_solve returns (_impl/sym.py:398) --
+    go to the library with their element stride; no AoS copy is made."""
+    from nitorch_fastmath_b200 import _dispatch as D
+    dtype = torch.float32
+    nn = n * (n + 1) // 2
+    shape = (24, 20, 18)
+    mat = G.spd_packed(shape, n, dtype, seed=1)
+    vec = G.vectors(shape, n, dtype, seed=2)
+    mat_cf = mat.to(DEV).movedim(-1, 0).contiguous()       # (NN, X, Y, Z)
+    vec_cf = vec.to(DEV).movedim(-1, 0).contiguous()       # (N, X, Y, Z)
+    m_view, v_view = mat_cf.movedim(0, -1), vec_cf.movedim(0, -1)
+    op = D.as_operand(m_view, shape, 1, dtype, allow_estride=True)
+    assert op.ptr == mat_cf.data_ptr() and op.stride == 1 and op.estride == 24 * 20 * 18
+    close(nfm.sym_solve(m_view, v_view), P.sym_solve(mat, vec), dtype)
+    close(nfm.sym_matvec(m_view, v_view), P.sym_matvec(mat, vec), dtype)
+    close(nfm.sym_invert(m_view), P.sym_invert(mat), dtype)
+    # mixed: AoS matrix, SoA vector, SoA output written in place
+    out_cf = torch.empty_like(vec_cf)
+    res = nfm.sym_solve(mat.to(DEV), v_view, out=out_cf.movedim(0, -1))
+    assert res.data_ptr() == out_cf.data_ptr()
+    close(out_cf.movedim(0, -1), P.sym_solve(mat, vec), dtype)
+    # in place on a channel-first field
+    nfm.sym_solve_(m_view, v_view)
+    close(vec_cf.movedim(0, -1), P.sym_solve(mat, vec), dtype)
+
+
 def test_dtype_semantics(nfm):
     mat = G.spd_packed(300, 3, torch.float64, seed=1)
     vec = G.vectors(300, 3, torch.float32, seed=2)
@@ -523,3 +552,21 @@ def test_host_pipeline(nfm, n):
     assert torch.equal(y, nfm.sym_matvec(mat.to(DEV), vec.to(DEV)).cpu())
     # non-plain host operands take the whole-upload path
     close(nfm.sym_solve(mat[:1000, :], vec[0]), P.sym_solve(mat[:1000], vec[0]), dtype)
+
+
+def test_single_process_multi_gpu_host_sharding(nfm):
+    """nitorch_fastmath_b200.multi_gpu: one process, the batch cut into slabs,
+    one host pipeline per device (all visible devices; 1 on a single-GPU box)."""
+    from nitorch_fastmath_b200 import multi_gpu
+    n, batch = 3, 3_000_017
+    mat = G.spd_packed(batch, n, torch.float32, seed=1).pin_memory()
+    vec = G.vectors(batch, n, torch.float32, seed=2).pin_memory()
+    x = multi_gpu.sym_solve_multi(mat, vec)
+    ref = nfm.sym_solve(mat.to(DEV), vec.to(DEV)).cpu()
+    assert torch.equal(x, ref)                                  # slabs are independent: bit-identical
+    sl = slice(batch // 2 - 5000, batch // 2 + 5000)            # straddles the 2-GPU slab boundary
+    close(x[sl], P.sym_solve(mat[sl], vec[sl]), torch.float32)
+    assert torch.equal(multi_gpu.sym_invert_multi(mat), nfm.sym_invert(mat.to(DEV)).cpu())
+    assert torch.equal(multi_gpu.sym_matvec_multi(mat, vec), nfm.sym_matvec(mat.to(DEV), vec.to(DEV)).cpu())
+    if torch.cuda.device_count() > 1:
+        assert torch.equal(multi_gpu.sym_solve_multi(mat, vec, devices=[1]), ref)
