@@ -53,8 +53,8 @@ extern "C" {
 #define NFM_LAYOUT_FULL 3            /* N*N row-major      */
 
 /* factorisation used by solve / invert */
-#define NFM_ALGO_AUTO 0 /* sym: closed form N<=4, LDL^T above; dense: closed form n<=3 (inverse/det), pivoted LU above */
-#define NFM_ALGO_LDL 1  /* LDL^T / Cholesky-type, no pivoting (SPD or strongly regular input) */
+#define NFM_ALGO_AUTO 0 /* sym: closed form N<=4; above, LDL^T with a per-matrix pivot check and pivoted-LU fallback (SPD at LDL^T speed, indefinite as the reference); dense: closed form n<=3 (inverse/det), pivoted LU above */
+#define NFM_ALGO_LDL 1  /* LDL^T / Cholesky-type, no pivoting, no check (SPD or strongly regular input) */
 #define NFM_ALGO_LU 2   /* LU with partial pivoting (any invertible input) */
 #define NFM_ALGO_WARP 3 /* sym_solve only: sub-warp cooperative elimination with shuffles (5 <= N <= 10), A/B variant */
 

@@ -165,7 +165,9 @@ int nfm_sym_solve_ex(int dtype, int n, int layout, int algo, int64_t batch, cons
     return finish(dtype == NFM_F32 ? sym_solve_part2<float>(n, a.p, s) : sym_solve_part2<double>(n, a.p, s));
   if (algo == NFM_ALGO_WARP)
     return finish(dtype == NFM_F32 ? sym_solve_warp<float>(n, a.p, s) : sym_solve_warp<double>(n, a.p, s));
-  return finish(dtype == NFM_F32 ? sym_solve_part1<float>(n, a.p, s) : sym_solve_part1<double>(n, a.p, s));
+  if (algo == NFM_ALGO_LDL)
+    return finish(dtype == NFM_F32 ? sym_solve_part1<float>(n, a.p, s) : sym_solve_part1<double>(n, a.p, s));
+  return finish(dtype == NFM_F32 ? sym_solve_part3<float>(n, a.p, s) : sym_solve_part3<double>(n, a.p, s));
 }
 
 int nfm_sym_solve(int dtype, int n, int layout, int algo, int64_t batch, const void* mat, int64_t mat_stride,
@@ -188,7 +190,9 @@ int nfm_sym_invert_ex(int dtype, int n, int algo, int diag_only, int64_t batch, 
   auto s = static_cast<cudaStream_t>(stream);
   if (algo == NFM_ALGO_LU && n > 4)
     return finish(dtype == NFM_F32 ? sym_invert_part1<float>(n, diag_only, a.p, s) : sym_invert_part1<double>(n, diag_only, a.p, s));
-  // NFM_ALGO_WARP has no invert kernel: LDL^T thread-per-matrix
+  if (algo == NFM_ALGO_AUTO && n > 4)
+    return finish(dtype == NFM_F32 ? sym_invert_part2<float>(n, diag_only, a.p, s) : sym_invert_part2<double>(n, diag_only, a.p, s));
+  // N <= 4 closed forms; NFM_ALGO_LDL; NFM_ALGO_WARP has no invert kernel: plain LDL^T
   return finish(dtype == NFM_F32 ? sym_invert_part0<float>(n, diag_only, a.p, s) : sym_invert_part0<double>(n, diag_only, a.p, s));
 }
 

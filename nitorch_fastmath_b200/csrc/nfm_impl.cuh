@@ -11,17 +11,21 @@ namespace nfm {
 template <typename T> int sym_matvec_impl(int n, int layout, const KParams& p, cudaStream_t s);
 
 // sym_solve: part 0 = layouts E, D, F and packed N <= 4 (closed forms);
-// part 1 = packed N 5..10 LDL^T; part 2 = packed N 5..10 pivoted LU
+// part 1 = packed N 5..10 LDL^T; part 2 = packed N 5..10 pivoted LU;
+// part 3 = packed N 5..10 AUTO (checked LDL^T with per-matrix LU fallback)
 template <typename T> int sym_solve_part0(int n, int layout, const KParams& p, cudaStream_t s);
 template <typename T> int sym_solve_part1(int n, const KParams& p, cudaStream_t s);
 template <typename T> int sym_solve_part2(int n, const KParams& p, cudaStream_t s);
+template <typename T> int sym_solve_part3(int n, const KParams& p, cudaStream_t s);
 
 // NFM_ALGO_WARP: sub-warp cooperative shuffle solve, packed N 5..10 (nfm_sym_warp.cu)
 template <typename T> int sym_solve_warp(int n, const KParams& p, cudaStream_t s);
 
-// sym_invert: part 0 = N <= 4 closed form + N 5..10 LDL^T; part 1 = N 5..10 pivoted LU
+// sym_invert: part 0 = N <= 4 closed form + N 5..10 LDL^T; part 1 = N 5..10 pivoted LU;
+// part 2 = N 5..10 AUTO (checked LDL^T with per-matrix Gauss-Jordan fallback)
 template <typename T> int sym_invert_part0(int n, int diag_only, const KParams& p, cudaStream_t s);
 template <typename T> int sym_invert_part1(int n, int diag_only, const KParams& p, cudaStream_t s);
+template <typename T> int sym_invert_part2(int n, int diag_only, const KParams& p, cudaStream_t s);
 
 // dense: part 0 = inverse (closed / Gauss-Jordan), part 1 = inverse (LDL^T) + det + matvec,
 // part 2 = solve LU, part 3 = solve LDL^T

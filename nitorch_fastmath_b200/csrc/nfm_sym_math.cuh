@@ -27,6 +27,9 @@ __host__ __device__ constexpr int pidx(int n, int i, int j) {
 template <typename T>
 __device__ __forceinline__ T sq(T x) { return x * x; }
 
+template <typename T>
+__device__ __forceinline__ T tabs(T x) { return x < T(0) ? -x : x; }
+
 // ---------------------------------------------------------------------------
 // y = A v      (_impl/sym.py:88-131)
 // ---------------------------------------------------------------------------
@@ -195,6 +198,35 @@ struct LDL {
     }
   }
 
+  // Same factorisation, but reports whether every 1x1 pivot was acceptable:
+  // |d_k| >= kPivotTol * max_i |a_ki| of the current Schur complement (the
+  // Bunch-Kaufman style test that bounds element growth) and finite.  SPD
+  // matrices always pass; a symmetric indefinite matrix that fails is re-solved
+  // with pivoted LU by the caller, which is what the reference does for every
+  // matrix of order > 4 (_impl/sym.py:392-396).
+  static constexpr float kPivotTol = 0.1f;
+  __device__ __forceinline__ bool factor_checked() {
+    // branch-free: one running minimum of the pivot margins, tested once at the end
+    // (fmax / fabs map to one FMNMX / DMNMX with an |x| source modifier each)
+    T worst = fabs(w[0][0]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      T big = T(0);
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) big = fmax(big, fabs(w[k][i]));
+      worst = fmin(worst, fabs(w[k][k]) - T(kPivotTol) * big);
+      rd[k] = T(1) / w[k][k];
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const T lik = w[k][i] * rd[k];
+#pragma unroll
+        for (int j = i; j < N; ++j) w[i][j] -= lik * w[k][j];
+        w[k][i] = lik;
+      }
+    }
+    return worst >= T(0);
+  }
+
   __device__ __forceinline__ void solve(const T (&v)[N], T (&x)[N]) const {
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = v[i];
@@ -244,9 +276,6 @@ struct LDL {
 // [A | B], R right-hand-side columns; registers only, predicated row swaps.
 // Used by: sym solve/invert with NFM_ALGO_LU, dense solve / inverse / det.
 // ---------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ T tabs(T x) { return x < T(0) ? -x : x; }
-
 template <typename T, int N, int R>
 struct GaussPP {
   T a[N][N];

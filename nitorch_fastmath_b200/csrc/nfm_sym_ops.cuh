@@ -80,11 +80,18 @@ struct SymSolveOp {
         sym_solve_closed<T, N>(m, v, x);
       } else if constexpr (ALGO == NFM_ALGO_LU) {
         sym_solve_lu<T, N>(m, v, x);
-      } else {
+      } else if constexpr (ALGO == NFM_ALGO_LDL) {
         LDL<T, N> f;
         f.load_packed(m);
         f.factor();
         f.solve(v, x);
+      } else {
+        // NFM_ALGO_AUTO: LDL^T with a pivot check; the rare matrix that fails
+        // it (indefinite / tiny pivot) is redone with pivoted LU
+        LDL<T, N> f;
+        f.load_packed(m);
+        if (f.factor_checked()) f.solve(v, x);
+        else sym_solve_lu<T, N>(m, v, x);
       }
     } else {
       GaussPP<T, N, 1> g;
@@ -143,11 +150,32 @@ struct SymInvertOp {
           // reference takes entry (j, i) of solve(A, e_i): column i, row j >= i
           out[DIAG_ONLY ? i : pidx(N, i, j)] = g.a[j][i];
         }
-    } else {
+    } else if constexpr (ALGO == NFM_ALGO_LDL) {
       LDL<T, N> f;
       f.load_packed(m);
       f.factor();
       f.template invert<DIAG_ONLY>(out);
+    } else {
+      // NFM_ALGO_AUTO: checked LDL^T, pivoted Gauss-Jordan for the matrices that fail
+      LDL<T, N> f;
+      f.load_packed(m);
+      if (f.factor_checked()) {
+        f.template invert<DIAG_ONLY>(out);
+      } else {
+        GaussJordan<T, N> g;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = 0; j < N; ++j) g.a[i][j] = m[pidx(N, i, j)];
+        g.invert();
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = i; j < N; ++j) {
+            if (DIAG_ONLY && j != i) continue;
+            out[DIAG_ONLY ? i : pidx(N, i, j)] = g.a[j][i];
+          }
+      }
     }
   }
 };

@@ -31,12 +31,18 @@ int sym_solve_part1(int n, const KParams& p, cudaStream_t s) {
   return DispatchN<SolveBind<T, NFM_LAYOUT_SYM, NFM_ALGO_LDL>::template Op, 5, NFM_MAX_N>::run(n, p, s);
 }
 template int sym_solve_part1<NFM_SCALAR>(int, const KParams&, cudaStream_t);
-#else
+#elif NFM_PART == 2
 template <typename T>
 int sym_solve_part2(int n, const KParams& p, cudaStream_t s) {
   return DispatchN<SolveBind<T, NFM_LAYOUT_SYM, NFM_ALGO_LU>::template Op, 5, NFM_MAX_N>::run(n, p, s);
 }
 template int sym_solve_part2<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+#else
+template <typename T>
+int sym_solve_part3(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<SolveBind<T, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>::template Op, 5, NFM_MAX_N>::run(n, p, s);
+}
+template int sym_solve_part3<NFM_SCALAR>(int, const KParams&, cudaStream_t);
 #endif
 
 }  // namespace nfm

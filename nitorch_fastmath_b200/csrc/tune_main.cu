@@ -110,79 +110,25 @@ int main(int argc, char** argv) {
 
   auto want = [&](const char* n) { return only[0] == 0 || strstr(n, only) != nullptr; };
 
-  for (int rep = 0; rep < 2; ++rep) {
-  if (want("solve3")) {
-    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
-    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
-    CFG(Op, "sym_solve3", 512, 2, 3, false, 48);
-    release(buf);
-  }
-  if (want("solve6")) {
-    using Op = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+  {
     Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 6, 6);
-    CFG(Op, "sym_solve6", 256, 2, 2, false, 132);
+    using A = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+    using B = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    CFG(A, "solve6 ldl", 256, 2, 2, false, 132);
+    CFG(B, "solve6 auto", 256, 2, 2, false, 132);
+    CFG(B, "solve6 auto", 256, 1, 3, false, 132);
+    CFG(B, "solve6 auto", 128, 1, 3, false, 132);
     release(buf);
   }
-  if (want("invert6")) {
-    using Op = SymInvertOp<float, 6, NFM_ALGO_LDL, false>;
-    Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 0, 21);
-    CFG(Op, "sym_invert6", 384, 1, 2, false, 168);
-    release(buf);
-  }
-  if (want("solve10")) {
-    using Op = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+  {
     Buffers buf = make<float>(160ll * 160 * 160, 55, 10, 10, 10);
-    CFG(Op, "sym_solve10", 256, 1, 2, false, 300);
+    using A = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+    using B = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    CFG(A, "solve10 ldl", 256, 1, 2, false, 300);
+    CFG(B, "solve10 auto", 256, 1, 2, false, 300);
+    CFG(B, "solve10 auto", 128, 1, 2, false, 300);
+    CFG(B, "solve10 auto", 128, 1, 3, false, 300);
     release(buf);
-  }
-  if (want("invert3")) {
-    using Op = SymInvertOp<float, 3, NFM_ALGO_LDL, false>;
-    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 0, 6);
-    CFG(Op, "sym_invert3", 512, 2, 3, false, 48);
-    release(buf);
-  }
-  if (want("invert10")) {
-    using Op = SymInvertOp<float, 10, NFM_ALGO_LDL, false>;
-    Buffers buf = make<float>(160ll * 160 * 160, 55, 10, 0, 55);
-    CFG(Op, "sym_invert10", 128, 1, 2, false, 440);
-    release(buf);
-  }
-  if (want("invert6d")) {
-    using Op = SymInvertOp<double, 6, NFM_ALGO_LDL, false>;
-    Buffers buf = make<double>(128ll * 128 * 128 * 2, 21, 6, 0, 21);
-    CFG(Op, "sym_invert6d", 128, 1, 2, false, 336);
-    release(buf);
-  }
-  if (want("inv4f")) {
-    using Op = BatchInvOp<float, 4, NFM_ALGO_AUTO>;
-    Buffers buf = make<float>(16ll << 20, 16, -4, 0, 16);
-    CFG(Op, "dense_inv4f", 128, 1, 3, true, 128);
-    release(buf);
-  }
-  if (want("inv3f")) {
-    using Op = BatchInvOp<float, 3, NFM_ALGO_AUTO>;
-    Buffers buf = make<float>(16ll << 20, 9, -3, 0, 9);
-    CFG(Op, "dense_inv3f", 384, 2, 3, false, 72);
-    release(buf);
-  }
-  if (want("matvec6")) {
-    using Op = SymMatvecOp<float, 6, NFM_LAYOUT_SYM>;
-    Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 6, 6);
-    CFG(Op, "sym_matvec6", 256, 2, 2, false, 132);
-    release(buf);
-  }
-  if (want("det4d")) {
-    using Op = BatchDetOp<double, 4>;
-    Buffers buf = make<double>(16ll << 20, 16, -4, 0, 1);
-    CFG(Op, "dense_det4d", 128, 2, 3, true, 136);
-    release(buf);
-  }
-  if (want("inv4d")) {
-    using Op = BatchInvOp<double, 4, NFM_ALGO_AUTO>;
-    Buffers buf = make<double>(16ll << 20, 16, -4, 0, 16);
-    CFG(Op, "dense_inv4d", 256, 1, 3, true, 256);
-    release(buf);
-  }
   }
   return 0;
 }

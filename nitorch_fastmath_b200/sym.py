@@ -197,9 +197,11 @@ def sym_solve(mat: Tensor, vec: Tensor,
 
     Reference: nitorch_fastmath/_impl/sym.py:327-398 (public name sym.py:33).
     Orders up to 4 use the reference's closed forms; orders 5..10 factorise
-    in registers (``method='ldl'``, default: LDL^T without pivoting, for SPD
-    / strongly regular matrices; ``method='lu'``: partial pivoting on the
-    expanded matrix, the reference's semantics for any invertible matrix).
+    in registers.  Default (``method='auto'``): LDL^T with a per-matrix pivot
+    check and a pivoted-LU fallback, so SPD fields run at LDL^T speed and
+    indefinite matrices get the reference's semantics.  ``method='ldl'``:
+    unchecked LDL^T; ``'lu'``: partial pivoting for every matrix (what the
+    reference does); ``'warp'``: the sub-warp cooperative A/B variant.
 
     Parameters
     ----------

@@ -60,8 +60,11 @@ def test_sym_golden(nfm, sym_golden, dtype, n):
     close(nfm.sym_invert(mat, True), sym_golden(f"{k}_invert_diag"), dtype)
     close(nfm.sym_invert(mat, method="lu"), sym_golden(f"{k}_invert"), dtype)
     close(nfm.sym_to_full(mat), sym_golden(f"{k}_full"), dtype, 2)
-    # symmetric indefinite: closed forms (n <= 4) / pivoted LU (n > 4), as the reference
-    close(nfm.sym_solve(sym_golden(f"{k}_ind_mat", DEV), vec, method="lu"), sym_golden(f"{k}_ind_solve"), dtype, scale=4)
+    # symmetric indefinite: closed forms (n <= 4) / pivoted LU (n > 4), as the reference;
+    # the default (checked LDL^T, LU fallback per matrix) must agree as well
+    ind = sym_golden(f"{k}_ind_mat", DEV)
+    close(nfm.sym_solve(ind, vec, method="lu"), sym_golden(f"{k}_ind_solve"), dtype, scale=4)
+    close(nfm.sym_solve(ind, vec), sym_golden(f"{k}_ind_solve"), dtype, scale=20)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -422,6 +425,30 @@ def test_compact_layouts(nfm, n):
         flat = full.reshape(3000, n * n)
         close(nfm.sym_matvec(flat.to(DEV), dv), P.batchmatvec(full, vec), dtype)
         close(nfm.sym_solve(flat.to(DEV), dv), P.solvevec(full, vec), dtype)
+
+
+@pytest.mark.parametrize("n", [5, 6, 8, 10])
+def test_indefinite_and_zero_pivot_matrices_default_method(nfm, n):
+    """The reference solves any invertible symmetric matrix of order > 4 (pivoted
+    LU).  Plain LDL^T breaks on a zero leading pivot; the default method detects
+    it per matrix and falls back, `method='ldl'` does not."""
+    dtype = torch.float64
+    batch = 4096
+    ind = G.sym_indefinite_packed(batch, n, dtype, seed=n)
+    vec = G.vectors(batch, n, dtype, seed=n + 1)
+    want = P.sym_solve(ind, vec)
+    close(nfm.sym_solve(ind.to(DEV), vec.to(DEV)), want, dtype, scale=1e3)
+    inv_want = P.sym_invert(ind)
+    close(nfm.sym_invert(ind.to(DEV)), inv_want, dtype, scale=1e3)
+    # a_00 = 0 exactly: [[0, 1], [1, 0]] (+) I
+    hard = torch.zeros(batch, n * (n + 1) // 2, dtype=dtype)
+    hard[:, 1:n] = 1.0
+    hard[:, n] = 1.0          # a_01
+    want = P.sym_solve(hard, vec)
+    got = nfm.sym_solve(hard.to(DEV), vec.to(DEV))
+    close(got, want, dtype, scale=10)
+    bad = nfm.sym_solve(hard.to(DEV), vec.to(DEV), method="ldl")
+    assert not torch.isfinite(bad).all()
 
 
 def test_singular_does_not_trap(nfm):
