@@ -336,7 +336,7 @@ constexpr int pick_tile(int stages, int in_bytes, int out_bytes) {
   return 64;
 }
 
-constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile == 512 ? 256 : tile; }  // MPT <= 8
+constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile; }  // one matrix per thread up to 512; MPT <= 8
 
 // Compute-heavy ops (pivoted elimination, Gauss-Jordan: Op::kHeavy) are bound by
 // the latency of their dependent chains rather than by HBM alone; they do best

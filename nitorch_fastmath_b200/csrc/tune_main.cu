@@ -112,22 +112,25 @@ int main(int argc, char** argv) {
 
   {
     Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 6, 6);
-    using A = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
     using B = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(A, "solve6 ldl", 256, 2, 2, false, 132);
     CFG(B, "solve6 auto", 256, 2, 2, false, 132);
-    CFG(B, "solve6 auto", 256, 1, 3, false, 132);
-    CFG(B, "solve6 auto", 128, 1, 3, false, 132);
+    CFG(B, "solve6 auto", 512, 1, 2, false, 132);
+    CFG(B, "solve6 auto", 384, 1, 2, false, 132);
+    CFG(B, "solve6 auto", 384, 1, 3, false, 132);
+    CFG(B, "solve6 auto", 384, 2, 2, false, 132);
+    CFG(B, "solve6 auto", 256, 1, 2, false, 132);
+    CFG(B, "solve6 auto", 192, 2, 2, false, 132);
+    CFG(B, "solve6 auto", 192, 2, 3, false, 132);
+    CFG(B, "solve6 auto", 320, 1, 3, false, 132);
     release(buf);
   }
   {
-    Buffers buf = make<float>(160ll * 160 * 160, 55, 10, 10, 10);
-    using A = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
-    using B = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(A, "solve10 ldl", 256, 1, 2, false, 300);
-    CFG(B, "solve10 auto", 256, 1, 2, false, 300);
-    CFG(B, "solve10 auto", 128, 1, 2, false, 300);
-    CFG(B, "solve10 auto", 128, 1, 3, false, 300);
+    Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 0, 21);
+    using B = SymInvertOp<float, 6, NFM_ALGO_AUTO, false>;
+    CFG(B, "invert6 auto", 384, 1, 2, false, 168);
+    CFG(B, "invert6 auto", 256, 1, 2, false, 168);
+    CFG(B, "invert6 auto", 512, 1, 2, false, 168);
+    CFG(B, "invert6 auto", 256, 2, 2, false, 168);
     release(buf);
   }
   return 0;
