@@ -181,7 +181,8 @@ int nfm_sym_outer(int dtype, int n, int64_t batch,
  * d(d+1)/2) -- the documented meaning of sym_matmul (_impl/sym.py:637-656)
  * and what its general branch jhjn computes (:596-634).
  * mode 1: out = J H J^T  (k == d) -- what the reference's unrolled branches
- * jhj1/2/3 compute for k == d <= 3 (:532-593).  1 <= k, d <= 4.
+ * jhj1/2/3 compute for k == d <= 3 (:532-593).  1 <= k, d <= 10 (register
+ * kernels up to 4 x 4, a run-time-sized kernel above).
  * Replaces sym_matmul _impl/sym.py:637-670. */
 int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch,
                    const void *jac, int64_t jac_stride,

@@ -1,6 +1,7 @@
 // nfm_extra.cu -- the remaining public names of nitorch_fastmath/sym.py:29
 // (SURVEY.md section 8f "next" rows): sym_det, sym_to_full, sym_outer.
 #include "nfm_dense_ops.cuh"
+#include "nfm_impl.cuh"
 #include "nfm_pipeline.cuh"
 #include "nfm_sym_ops.cuh"
 
@@ -163,11 +164,18 @@ int nfm_sym_outer(int dtype, int n, int64_t batch, const void* vec, int64_t vec_
 int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch, const void* jac, int64_t jac_stride, const void* hess,
                    int64_t hess_stride, void* out, int64_t out_stride, void* stream) {
   if (dtype != NFM_F32 && dtype != NFM_F64) { set_error("dtype must be NFM_F32 or NFM_F64"); return NFM_E_UNSUPPORTED; }
-  if (k < 1 || k > 4 || d < 1 || d > 4 || (mode != 0 && mode != 1) || (mode == 1 && k != d)) {
-    set_error("sym_matmul: 1 <= k, d <= 4; mode 1 needs k == d");
+  if (k < 1 || k > NFM_MAX_N || d < 1 || d > NFM_MAX_N || (mode != 0 && mode != 1) || (mode == 1 && k != d)) {
+    set_error("sym_matmul: 1 <= k, d <= 10; mode 1 needs k == d");
     return NFM_E_UNSUPPORTED;
   }
   if (batch < 0 || !jac || !hess || !out || jac_stride < 0 || hess_stride < 0 || out_stride < 0) { set_error("bad argument"); return NFM_E_BADARG; }
+  if (k > 4 || d > 4) {  // run-time-sized kernel above the templated 4 x 4
+    auto st = static_cast<cudaStream_t>(stream);
+    const int rc = dtype == NFM_F32 ? sym_matmul_rt<float>(k, d, mode, batch, jac, jac_stride, hess, hess_stride, out, out_stride, st)
+                                    : sym_matmul_rt<double>(k, d, mode, batch, jac, jac_stride, hess, hess_stride, out, out_stride, st);
+    if (rc) set_error("sym_matmul kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
+    return rc;
+  }
   KParams p{};
   p.in[0].ptr = jac;
   p.in[0].stride = jac_stride;

@@ -85,6 +85,51 @@ __global__ void __launch_bounds__(128) solve_rt_kernel(const T* mat, i64 as, con
   }
 }
 
+// J^T H J (mode 0) or J H J^T (mode 1, k == d) for any 1 <= k, d <= 10:
+// run-time-sized fallback of the templated SymMatmulOp (k, d <= 4)
+template <typename T>
+__global__ void __launch_bounds__(128) matmul_rt_kernel(const T* __restrict__ jac, i64 js, const T* __restrict__ hess, i64 hs,
+                                                        T* __restrict__ out, i64 os, int k, int d, int mode, i64 batch) {
+  const int hn = mode == 0 ? k : d;  // order of H
+  const int on = mode == 0 ? d : k;  // order of the result
+  for (i64 b = i64(blockIdx.x) * blockDim.x + threadIdx.x; b < batch; b += i64(gridDim.x) * blockDim.x) {
+    const T* j = jac + b * js;
+    const T* h = hess + b * hs;
+    T hj[NFM_MAX_N][NFM_MAX_N];
+    for (int a = 0; a < hn; ++a)
+      for (int o = 0; o < on; ++o) {
+        T s = T(0);
+        for (int c = 0; c < hn; ++c) {
+          const int lo = a < c ? a : c, hi = a < c ? c : a;
+          const int idx = lo == hi ? lo : hn + lo * hn - (lo * (lo + 1)) / 2 + (hi - lo - 1);
+          s += h[idx] * (mode == 0 ? j[c * d + o] : j[o * d + c]);
+        }
+        hj[a][o] = s;
+      }
+    T* dst = out + b * os;
+    for (int o = 0; o < on; ++o)
+      for (int q = o; q < on; ++q) {
+        T s = T(0);
+        for (int a = 0; a < hn; ++a) s += (mode == 0 ? j[a * d + o] : j[o * d + a]) * hj[a][q];
+        dst[o == q ? o : on + o * on - (o * (o + 1)) / 2 + (q - o - 1)] = s;
+      }
+  }
+}
+
+static unsigned grid_for(i64 work);
+
+template <typename T>
+int sym_matmul_rt(int k, int d, int mode, i64 batch, const void* jac, i64 js, const void* hess, i64 hs, void* out, i64 os,
+                  cudaStream_t s) {
+  if (batch == 0) return 0;
+  matmul_rt_kernel<T><<<grid_for(batch), 128, 0, s>>>(static_cast<const T*>(jac), js, static_cast<const T*>(hess), hs,
+                                                      static_cast<T*>(out), os, k, d, mode, batch);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+template int sym_matmul_rt<float>(int, int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
+template int sym_matmul_rt<double>(int, int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
+
 static unsigned grid_for(i64 work) {
   i64 blocks = (work + 127) / 128;
   const i64 cap = i64(device_info().sm_count) * 16;

@@ -44,4 +44,8 @@ template <typename T>
 int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out, i64 os,
                    cudaStream_t s);
 
+template <typename T>
+int sym_matmul_rt(int k, int d, int mode, i64 batch, const void* jac, i64 js, const void* hess, i64 hs, void* out, i64 os,
+                  cudaStream_t s);
+
 }  // namespace nfm

@@ -423,8 +423,8 @@ def sym_matmul(j: Tensor, h: Tensor) -> Tensor:
         (dj, dh), _ = _to_device_inputs(j, h)
         return sym_matmul(dj, dh).cpu()
     k, d = j.shape[-2:]
-    if not (1 <= k <= 4 and 1 <= d <= 4):
-        raise ValueError("sym_matmul supports 1 <= k, d <= 4")
+    if not (1 <= k <= _lib.MAX_N and 1 <= d <= _lib.MAX_N):
+        raise ValueError(f"sym_matmul supports 1 <= k, d <= {_lib.MAX_N}")
     if h.shape[-1] != k * (k + 1) // 2:
         raise ValueError("only compact symmetric h (k*(k+1)//2 coefficients) is supported")
     cdt = h.dtype if h.dtype in (torch.float32, torch.float64) else D.compute_dtype(j, h)

@@ -61,5 +61,6 @@ def test_argument_validation_without_a_gpu():
     assert b"sign" in lib.nfm_last_error_string()
     assert lib.nfm_batch_solve(_lib.F64, 4, 0, 0, 4, p, 16, p, 4, p, 4, None) == -2
     assert lib.nfm_sym_matmul(_lib.F32, 2, 3, 1, 4, p, 6, p, 3, p, 6, None) == -1
+    assert lib.nfm_sym_matmul(_lib.F32, 11, 3, 0, 4, p, 33, p, 66, p, 6, None) == -1
     with pytest.raises(_lib.NfmError):
         _lib.check(-2, "demo")

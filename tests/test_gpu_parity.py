@@ -462,7 +462,7 @@ def test_singular_does_not_trap(nfm):
 
 def test_sym_matmul(nfm):
     dtype = torch.float64
-    for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1)]:
+    for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1), (6, 6), (5, 3), (3, 7), (10, 10)]:
         j = G.vectors((2000, k), d, dtype, seed=k * 10 + d)
         h = G.spd_packed(2000, k, dtype, seed=k)
         hf = P.sym_to_full(h)
