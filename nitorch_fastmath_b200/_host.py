@@ -10,6 +10,7 @@ computed with the device entry point and downloaded.
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from typing import Optional
 
@@ -17,8 +18,8 @@ import torch
 
 from . import _lib
 
-_DEFAULT_CHUNK_BYTES = 32 << 20   # per pipeline stage, inputs + output
-_NBUF = 3
+_DEFAULT_CHUNK_BYTES = int(os.environ.get("NFM_HOST_CHUNK_MB", "16")) << 20   # per pipeline stage, inputs + output
+_NBUF = int(os.environ.get("NFM_HOST_NBUF", "3"))
 
 
 class _DeviceState:

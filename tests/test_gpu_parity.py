@@ -597,3 +597,64 @@ def test_single_process_multi_gpu_host_sharding(nfm):
     assert torch.equal(multi_gpu.sym_matvec_multi(mat, vec), nfm.sym_matvec(mat.to(DEV), vec.to(DEV)).cpu())
     if torch.cuda.device_count() > 1:
         assert torch.equal(multi_gpu.sym_solve_multi(mat, vec, devices=[1]), ref)
+
+
+def _random_view(t, rng):
+    """A random view / re-layout of ``t`` with the same values and shape."""
+    kind = rng.choice(["plain", "channel_first", "sliced", "transposed_batch", "offset", "double"])
+    if kind == "channel_first":
+        return t.movedim(-1, 0).contiguous().movedim(0, -1)
+    if kind == "sliced":                       # every second element of a wider buffer
+        wide = torch.zeros(*t.shape[:-1], 2 * t.shape[-1], device=t.device, dtype=t.dtype)
+        wide[..., ::2] = t
+        return wide[..., ::2]
+    if kind == "transposed_batch" and t.dim() >= 3:
+        return t.transpose(0, 1).contiguous().transpose(0, 1)
+    if kind == "offset":                       # storage offset that breaks 16-byte alignment
+        flat = torch.zeros(t.numel() + 1, device=t.device, dtype=t.dtype)
+        flat[1:] = t.reshape(-1)
+        return flat[1:].view(t.shape)
+    if kind == "double":
+        return t.double()
+    return t
+
+
+def test_randomised_shapes_views_and_broadcasting(nfm):
+    """60 seeded random cases: order, batch shape, which operand is broadcast,
+    memory layout of every operand, regulariser kind -- all against the oracle."""
+    import random
+    rng = random.Random(1234)
+    for case in range(60):
+        n = rng.randint(1, 10)
+        nb = rng.randint(1, 3)
+        batch = tuple(rng.choice([1, 2, 3, 5, 17, 64]) for _ in range(nb))
+        if rng.random() < 0.25:
+            batch = (rng.choice([700, 1500, 4099]),)         # long enough for TMA tiles + ragged tail
+        mat = G.spd_packed(batch, n, torch.float32, seed=case)
+        vec = G.vectors(batch, n, torch.float32, seed=1000 + case)
+        # broadcast one operand along a random subset of batch dims
+        if rng.random() < 0.4:
+            which = rng.choice(["mat", "vec"])
+            idx = tuple(slice(0, 1) if rng.random() < 0.6 else slice(None) for _ in batch)
+            if which == "mat":
+                mat = mat[idx]
+            else:
+                vec = vec[idx]
+        reg_kind = rng.choice([None, None, "scalar", "vector", "field"])
+        reg = {None: None, "scalar": 0.3, "vector": [0.5, 0.1][:min(n, 2)],
+               "field": G.vectors(torch.broadcast_shapes(mat.shape[:-1], vec.shape[:-1]), n, torch.float32, seed=case).abs()}[reg_kind]
+        want = P.sym_solve(mat, vec, reg)
+        dm, dv = _random_view(mat.to(DEV), rng), _random_view(vec.to(DEV), rng)
+        dr = reg.to(DEV) if torch.is_tensor(reg) else reg
+        got = nfm.sym_solve(dm, dv, dr)
+        tol_dtype = torch.float32
+        assert tuple(got.shape) == tuple(want.shape), (case, got.shape, want.shape)
+        err = G.rel_err(got, want)
+        assert err <= TOL[tol_dtype], (case, n, batch, err)
+        # matvec of the solution gives the right-hand side back (shape semantics of matvec)
+        full_mat = mat.expand(*want.shape[:-1], mat.shape[-1])
+        if reg is None:
+            back = nfm.sym_matvec(_random_view(full_mat.contiguous().to(DEV), rng), got)
+            assert G.rel_err(back, vec.expand_as(want)) <= 5e-5, (case, n)
+        inv = nfm.sym_invert(_random_view(mat.to(DEV), rng))
+        assert G.rel_err(inv, P.sym_invert(mat)) <= TOL[torch.float32], (case, n)
