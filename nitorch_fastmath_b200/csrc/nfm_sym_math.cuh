@@ -206,25 +206,49 @@ struct LDL {
   // matrix of order > 4 (_impl/sym.py:392-396).
   static constexpr float kPivotTol = 0.1f;
   __device__ __forceinline__ bool factor_checked() {
-    // branch-free: one running minimum of the pivot margins, tested once at the end
-    // (fmax / fabs map to one FMNMX / DMNMX with an |x| source modifier each)
-    T worst = fabs(w[0][0]);
+    if constexpr (sizeof(T) == 8) {
+      // fp64: do the magnitude bookkeeping on the high words as integers (the
+      // ordering of |x| is the ordering of its exponent/top-mantissa bits; the
+      // tolerance 2^-3 is a subtraction in the exponent field): full-rate
+      // integer min/max instead of ~N*N/2 half-rate FP64 compares.
+      int worst = 0x7fffffff;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      T big = T(0);
+      for (int k = 0; k < N; ++k) {
+        int big = 0;
 #pragma unroll
-      for (int i = k + 1; i < N; ++i) big = fmax(big, fabs(w[k][i]));
-      worst = fmin(worst, fabs(w[k][k]) - T(kPivotTol) * big);
-      rd[k] = T(1) / w[k][k];
+        for (int i = k + 1; i < N; ++i) big = max(big, __double2hiint(w[k][i]) & 0x7fffffff);
+        worst = min(worst, (__double2hiint(w[k][k]) & 0x7fffffff) - big + (3 << 20));
+        rd[k] = T(1) / w[k][k];
 #pragma unroll
-      for (int i = k + 1; i < N; ++i) {
-        const T lik = w[k][i] * rd[k];
+        for (int i = k + 1; i < N; ++i) {
+          const T lik = w[k][i] * rd[k];
 #pragma unroll
-        for (int j = i; j < N; ++j) w[i][j] -= lik * w[k][j];
-        w[k][i] = lik;
+          for (int j = i; j < N; ++j) w[i][j] -= lik * w[k][j];
+          w[k][i] = lik;
+        }
       }
+      return worst >= 0;
+    } else {
+      // branch-free: one running minimum of the pivot margins, tested once at the
+      // end (fmax / fabs map to one FMNMX with an |x| source modifier each)
+      T worst = fabs(w[0][0]);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        T big = T(0);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) big = fmax(big, fabs(w[k][i]));
+        worst = fmin(worst, fabs(w[k][k]) - T(kPivotTol) * big);
+        rd[k] = T(1) / w[k][k];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+          const T lik = w[k][i] * rd[k];
+#pragma unroll
+          for (int j = i; j < N; ++j) w[i][j] -= lik * w[k][j];
+          w[k][i] = lik;
+        }
+      }
+      return worst >= T(0);
     }
-    return worst >= T(0);
   }
 
   __device__ __forceinline__ void solve(const T (&v)[N], T (&x)[N]) const {

@@ -112,25 +112,34 @@ int main(int argc, char** argv) {
 
   {
     Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 6, 6);
+    using A = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
     using B = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(B, "solve6 auto", 256, 2, 2, false, 132);
-    CFG(B, "solve6 auto", 512, 1, 2, false, 132);
-    CFG(B, "solve6 auto", 384, 1, 2, false, 132);
-    CFG(B, "solve6 auto", 384, 1, 3, false, 132);
-    CFG(B, "solve6 auto", 384, 2, 2, false, 132);
-    CFG(B, "solve6 auto", 256, 1, 2, false, 132);
-    CFG(B, "solve6 auto", 192, 2, 2, false, 132);
-    CFG(B, "solve6 auto", 192, 2, 3, false, 132);
-    CFG(B, "solve6 auto", 320, 1, 3, false, 132);
+    CFG(A, "solve6 f32 ldl", 512, 1, 2, false, 132);
+    CFG(B, "solve6 f32 auto", 512, 1, 2, false, 132);
     release(buf);
   }
   {
-    Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 0, 21);
-    using B = SymInvertOp<float, 6, NFM_ALGO_AUTO, false>;
-    CFG(B, "invert6 auto", 384, 1, 2, false, 168);
-    CFG(B, "invert6 auto", 256, 1, 2, false, 168);
-    CFG(B, "invert6 auto", 512, 1, 2, false, 168);
-    CFG(B, "invert6 auto", 256, 2, 2, false, 168);
+    Buffers buf = make<float>(160ll * 160 * 160, 55, 10, 10, 10);
+    using A = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+    using B = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    CFG(A, "solve10 f32 ldl", 256, 1, 2, false, 300);
+    CFG(B, "solve10 f32 auto", 256, 1, 2, false, 300);
+    release(buf);
+  }
+  {
+    Buffers buf = make<double>(128ll * 128 * 256, 55, 10, 10, 10);
+    using A = SymSolveOp<double, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+    using B = SymSolveOp<double, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    CFG(A, "solve10 f64 ldl", 128, 1, 2, false, 600);
+    CFG(B, "solve10 f64 auto", 128, 1, 2, false, 600);
+    release(buf);
+  }
+  {
+    Buffers buf = make<double>(128ll * 128 * 256, 45, 9, 9, 9);
+    using A = SymSolveOp<double, 9, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
+    using B = SymSolveOp<double, 9, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    CFG(A, "solve9 f64 ldl", 128, 1, 2, false, 504);
+    CFG(B, "solve9 f64 auto", 128, 1, 2, false, 504);
     release(buf);
   }
   return 0;
