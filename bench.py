@@ -356,7 +356,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and os.environ.get("NFM_BENCH_BIND") == "1":   # optional: measured no gain on this pool's hosts
         config["cpu_affinity"] = bind_to_gpu_cpus(local_rank)
     dist = None
     if world > 1:
