@@ -2,11 +2,13 @@
 
 torch is used for allocation, broadcasting metadata and the current stream
 only.  Every operand is handed to the library as (device pointer, batch
-stride in elements): its record dims (the last ``rec_ndim`` dims) must be
-contiguous and its batch dims must collapse to one stride -- 0 for a fully
-broadcast operand, ``record length`` for a dense one, anything else takes the
-library's strided kernel.  Operands that do not collapse are materialised
-with ``.contiguous()`` (one extra pass; documented in DESIGN.md).
+stride, element stride), all in elements: its batch dims must collapse to one
+stride -- 0 for a fully broadcast operand, ``record length`` for a dense one,
+anything else takes the library's strided kernel.  A 1-D record whose elements
+are not adjacent (a channel-first field viewed coefficient-last) is passed
+with its element stride; 2-D records must be contiguous.  Operands whose
+batch dims do not collapse are materialised with ``.contiguous()`` (one extra
+pass; documented in DESIGN.md).
 """
 from __future__ import annotations
 

@@ -106,40 +106,62 @@ void release(Buffers& b) {
 #define CFG(OP, NAME, THR, MPT, ST, SEG, BYTES) run_config<OP, THR, MPT, ST, SEG>(NAME, buf, BYTES)
 
 int main(int argc, char** argv) {
+  // usage: nfm_tune [substring]   -- run only the blocks whose name contains it
   const char* only = argc > 1 ? argv[1] : "";
-
   auto want = [&](const char* n) { return only[0] == 0 || strstr(n, only) != nullptr; };
 
-  {
+  // The three sweeps that produced the Tune<> rule are recorded in
+  // profiles/r1_tile_geometry_sweep.txt; this list is the regression check:
+  // the geometry the rule picks for each headline op next to its neighbours.
+  if (want("solve3")) {
+    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
+    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
+    CFG(Op, "sym_solve3", 512, 2, 3, false, 48);   // rule
+    CFG(Op, "sym_solve3", 256, 2, 3, false, 48);
+    CFG(Op, "sym_solve3", 256, 4, 4, false, 48);
+    CFG(Op, "sym_solve3", 1024, 1, 3, false, 48);
+    release(buf);
+  }
+  if (want("solve6")) {
+    using Op = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    using Ldl = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
     Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 6, 6);
-    using A = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
-    using B = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(A, "solve6 f32 ldl", 512, 1, 2, false, 132);
-    CFG(B, "solve6 f32 auto", 512, 1, 2, false, 132);
+    CFG(Op, "sym_solve6 auto", 512, 1, 2, false, 132);   // rule
+    CFG(Ldl, "sym_solve6 ldl", 512, 1, 2, false, 132);
+    CFG(Op, "sym_solve6 auto", 256, 2, 2, false, 132);
+    CFG(Op, "sym_solve6 auto", 384, 1, 3, false, 132);
     release(buf);
   }
-  {
+  if (want("invert6")) {
+    using Op = SymInvertOp<float, 6, NFM_ALGO_AUTO, false>;
+    Buffers buf = make<float>(192ll * 192 * 192, 21, 6, 0, 21);
+    CFG(Op, "sym_invert6 auto", 384, 1, 2, false, 168);  // rule
+    CFG(Op, "sym_invert6 auto", 256, 1, 2, false, 168);
+    CFG(Op, "sym_invert6 auto", 512, 1, 2, false, 168);
+    release(buf);
+  }
+  if (want("solve10")) {
+    using Op = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
     Buffers buf = make<float>(160ll * 160 * 160, 55, 10, 10, 10);
-    using A = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
-    using B = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(A, "solve10 f32 ldl", 256, 1, 2, false, 300);
-    CFG(B, "solve10 f32 auto", 256, 1, 2, false, 300);
+    CFG(Op, "sym_solve10 auto", 256, 1, 2, false, 300);  // rule
+    CFG(Op, "sym_solve10 auto", 128, 1, 2, false, 300);
+    CFG(Op, "sym_solve10 auto", 128, 1, 3, false, 300);
     release(buf);
   }
-  {
-    Buffers buf = make<double>(128ll * 128 * 256, 55, 10, 10, 10);
-    using A = SymSolveOp<double, 10, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
-    using B = SymSolveOp<double, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(A, "solve10 f64 ldl", 128, 1, 2, false, 600);
-    CFG(B, "solve10 f64 auto", 128, 1, 2, false, 600);
+  if (want("inv4d")) {
+    using Op = BatchInvOp<double, 4, NFM_ALGO_AUTO>;
+    Buffers buf = make<double>(16ll << 20, 16, -4, 0, 16);
+    CFG(Op, "dense_inv4d", 256, 1, 3, true, 256);   // pinned (TuneFixed)
+    CFG(Op, "dense_inv4d", 256, 1, 3, false, 256);  // dense layout: 8-way bank conflicts
+    CFG(Op, "dense_inv4d", 128, 1, 3, true, 256);
     release(buf);
   }
-  {
-    Buffers buf = make<double>(128ll * 128 * 256, 45, 9, 9, 9);
-    using A = SymSolveOp<double, 9, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
-    using B = SymSolveOp<double, 9, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
-    CFG(A, "solve9 f64 ldl", 128, 1, 2, false, 504);
-    CFG(B, "solve9 f64 auto", 128, 1, 2, false, 504);
+  if (want("solve4d")) {
+    using Op = BatchSolveOp<double, 4, NFM_ALGO_LU>;
+    Buffers buf = make<double>(16ll << 20, 16, -4, 4, 4);
+    CFG(Op, "dense_solve4d", 128, 1, 3, true, 192);  // pinned
+    CFG(Op, "dense_solve4d", 256, 1, 3, true, 192);
+    CFG(Op, "dense_solve4d", 512, 1, 2, true, 192);
     release(buf);
   }
   return 0;
