@@ -658,3 +658,35 @@ def test_randomised_shapes_views_and_broadcasting(nfm):
             assert G.rel_err(back, vec.expand_as(want)) <= 5e-5, (case, n)
         inv = nfm.sym_invert(_random_view(mat.to(DEV), rng))
         assert G.rel_err(inv, P.sym_invert(mat)) <= TOL[torch.float32], (case, n)
+
+
+def test_sugar_surface(nfm):
+    """lmdiv / rmdiv / inv / solvevec / matvec with `out=` and both methods
+    (reference sugar.py:75-341)."""
+    dtype = torch.float64
+    for n in (2, 3, 5, 8):
+        a = G.dense_shifted((6, 50), n, dtype, seed=n)
+        spd = G.dense_spd((6, 50), n, dtype, seed=n)
+        b = G.vectors((6, 50, 4), n, dtype, seed=n + 1)              # (…, k=4, n): right-division operand
+        rhs = b.transpose(-1, -2).contiguous()                        # (…, n, k)
+        da, ds, db, dr = a.to(DEV), spd.to(DEV), b.to(DEV), rhs.to(DEV)
+        close(nfm.lmdiv(da, dr), torch.linalg.solve(a, rhs), dtype, 2)
+        close(nfm.lmdiv(ds, dr, method="chol"), torch.linalg.solve(spd, rhs), dtype, 2)
+        close(nfm.rmdiv(db, da), b @ torch.linalg.inv(a), dtype, 2, scale=10)
+        out = torch.empty(6, 50, n, 4, device=DEV, dtype=dtype)
+        assert nfm.lmdiv(da, dr, out=out) is out
+        close(out, torch.linalg.solve(a, rhs), dtype, 2)
+        vec = G.vectors((6, 50), n, dtype, seed=n + 2)
+        o1 = torch.empty(6, 50, n, device=DEV, dtype=dtype)
+        assert nfm.solvevec(da, vec.to(DEV), out=o1).data_ptr() == o1.data_ptr()   # a squeezed view of out, as the reference
+        close(o1, P.solvevec(a, vec), dtype)
+        o2 = torch.empty(6, 50, n, device=DEV, dtype=dtype)
+        nfm.matvec(da, vec.to(DEV), out=o2)
+        close(o2, P.batchmatvec(a, vec), dtype)
+        o3 = torch.empty(6, 50, n, n, device=DEV, dtype=dtype)
+        nfm.inv(ds, "chol", out=o3)
+        close(o3, torch.linalg.inv(spd), dtype, 2)
+    with pytest.raises(NotImplementedError):
+        nfm.lmdiv(torch.zeros(3, 4, 5, device=DEV), torch.zeros(3, 4, 1, device=DEV))
+    with pytest.raises(NotImplementedError):
+        nfm.inv(torch.eye(3, device=DEV)[None], method="svd")
