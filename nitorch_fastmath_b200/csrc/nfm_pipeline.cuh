@@ -107,14 +107,23 @@ __device__ __forceinline__ int elem_offset(int e) {
 template <class G, int LEN>
 __device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typename G::T* src, int count) {
   using T = typename G::T;
-  for (int e = threadIdx.x; e < count * LEN; e += blockDim.x)
-    *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e)) = src[e];
+  constexpr int U = 4;  // independent loads in flight per thread
+  const int total = count * LEN, step = int(blockDim.x);
+  for (int e0 = threadIdx.x; e0 < total; e0 += U * step) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = (e0 + u * step < total) ? src[e0 + u * step] : T(0);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (e0 + u * step < total) *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e0 + u * step)) = v[u];
+  }
 }
 
 template <class G, int LEN>
 __device__ __forceinline__ void coop_store(typename G::T* dst, const unsigned char* smem_tile, int count) {
   using T = typename G::T;
-  for (int e = threadIdx.x; e < count * LEN; e += blockDim.x)
+  const int total = count * LEN;
+  for (int e = threadIdx.x; e < total; e += blockDim.x)
     dst[e] = *reinterpret_cast<const T*>(smem_tile + elem_offset<G, LEN>(e));
 }
 

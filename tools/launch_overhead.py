@@ -14,7 +14,7 @@ from nitorch_fastmath_b200 import _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
 n, nn = 3, 6
-for batch in (1024, 65536, 1 << 20, 2 << 20, 4 << 20):
+for batch in (1024, 65536, 1000000, 1 << 20, 2 << 20, 4 << 20):
     nsets = max(1, min(8, (400 << 20) // (batch * 48)))
     sets = []
     for s in range(nsets):
