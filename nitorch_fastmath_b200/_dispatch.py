@@ -175,3 +175,39 @@ def detect_layout(nn: int, n: int) -> int:
         return _lib.LAYOUT_FULL
     raise ValueError(f"matrix with {nn} coefficients does not match a vector of length {n}: "
                      f"expected 1, {n}, {n * (n + 1) // 2} or {n * n}")
+
+
+# --------------------------------------------------------------------------
+# fast path of the Python layer: dense CUDA operands with identical batch dims
+# (the common case) skip the broadcasting / collapsing machinery above
+# --------------------------------------------------------------------------
+
+def plain_cuda(ref: torch.Tensor, *others: Optional[torch.Tensor]) -> bool:
+    """All tensors are contiguous CUDA tensors on ref's device with ref's dtype
+    (float32 / float64) and ref's batch dims (all dims but the last)."""
+    if ref.device.type != "cuda" or ref.dtype not in _DTYPE_CODE or not ref.is_contiguous():
+        return False
+    lead = ref.shape[:-1]
+    for t in others:
+        if t is None:
+            continue
+        if t.device != ref.device or t.dtype != ref.dtype or not t.is_contiguous() or t.shape[:-1] != lead:
+            return False
+    return True
+
+
+class device_of:
+    """Make ``dev`` current for the duration of a launch -- without touching the
+    CUDA context when it already is (the usual case)."""
+    __slots__ = ("_ctx",)
+
+    def __init__(self, dev: torch.device):
+        self._ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)

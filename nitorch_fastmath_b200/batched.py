@@ -51,7 +51,7 @@ def batchdet(a: Tensor) -> Tensor:
     o, res, _ = D.out_operand(None, batch, 0, cdt, a.device)
     if nb > 0:
         m = D.as_operand(a, batch, 2, cdt)
-        with torch.cuda.device(a.device):
+        with D.device_of(a.device):
             rc = _lib.load().nfm_batch_det(D.dtype_code(cdt), n, nb, m.ptr, m.stride, o.ptr, o.stride,
                                            D.current_stream_ptr(a.device))
         _lib.check(rc, "nfm_batch_det")
@@ -89,7 +89,7 @@ def batchinv(a: Tensor, *, method: str = 'auto', regularise: bool = True) -> Ten
     o, res, _ = D.out_operand(None, (*batch, n, n), 2, cdt, a.device)
     if nb > 0:
         m = D.as_operand(a, batch, 2, cdt)
-        with torch.cuda.device(a.device):
+        with D.device_of(a.device):
             rc = _lib.load().nfm_batch_inv(D.dtype_code(cdt), n, algo, int(bool(regularise)), nb, m.ptr, m.stride,
                                            o.ptr, o.stride, D.current_stream_ptr(a.device))
         _lib.check(rc, "nfm_batch_inv")
@@ -124,7 +124,7 @@ def batchmatvec(mat: Tensor, vec: Tensor) -> Tensor:
     if nb > 0:
         a = D.as_operand(mat, batch, 2, cdt)
         v = D.as_operand(vec, batch, 1, cdt)
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = _lib.load().nfm_batch_matvec(D.dtype_code(cdt), m_, n, nb, a.ptr, a.stride, v.ptr, v.stride,
                                               o.ptr, o.stride, D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_batch_matvec")

@@ -60,7 +60,7 @@ def lmdiv(a: Tensor, b: Tensor, method: str = 'lu', rcond: float = 1e-15, out: O
     if nb > 0 and k > 0:
         ao = D.as_operand(a, batch, 2, cdt)
         bo = D.as_operand(b, batch, 2, cdt)
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = _lib.load().nfm_batch_solve(D.dtype_code(cdt), n, k, algo, nb, ao.ptr, ao.stride, bo.ptr, bo.stride,
                                              o.ptr, o.stride, D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_batch_solve")

@@ -71,6 +71,25 @@ def _to_device_inputs(*tensors):
 
 def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
             dtype: Optional[torch.dtype], out: Optional[Tensor]) -> Tensor:
+    if (dtype is None and torch.is_tensor(mat) and torch.is_tensor(vec) and D.plain_cuda(vec, mat, inp, out)
+            and (out is None or out.shape == vec.shape)):
+        # fast path: dense CUDA fields with the same batch dims
+        n = vec.shape[-1]
+        _check_n(n)
+        nn = mat.shape[-1]
+        layout = D.detect_layout(nn, n)
+        if inp is not None and inp.shape[-1] != n:
+            raise ValueError("inp and vec must have the same trailing size")
+        res = out if out is not None else torch.empty_like(vec)
+        nb = vec.numel() // n
+        if nb > 0:
+            with D.device_of(vec.device):
+                rc = _lib.load().nfm_sym_matvec(
+                    D.dtype_code(vec.dtype), n, layout, nb, mat.data_ptr(), nn, vec.data_ptr(), n,
+                    None if inp is None else inp.data_ptr(), 0 if inp is None else n, sign,
+                    res.data_ptr(), n, D.current_stream_ptr(vec.device))
+            _lib.check(rc, "nfm_sym_matvec")
+        return res
     mat, vec = torch.as_tensor(mat), torch.as_tensor(vec)
     tensors = [mat, vec] + ([inp] if inp is not None else [])
     dev = D.common_device(*tensors)
@@ -111,7 +130,7 @@ def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
         m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
         v = D.as_operand(vec, batch, 1, cdt, allow_estride=True)
         i = D.as_operand(inp, batch, 1, cdt, allow_estride=True) if inp is not None else None
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = _lib.load().nfm_sym_matvec_ex(
                 code, n, layout, nb, m.c_struct(), v.c_struct(), i.c_struct() if i is not None else None, sign,
                 o.c_struct(), D.current_stream_ptr(dev))
@@ -173,6 +192,9 @@ def sym_submatvec_(inp: Tensor, mat: Tensor, vec: Tensor, dtype: Optional[torch.
 # solve
 # ---------------------------------------------------------------------------
 
+_REG_CACHE = {}   # (values, n, dtype, device) -> device tensor; scalar regularisers recur every iteration
+
+
 def _as_diag(diag, n: int, dtype: torch.dtype, device: torch.device) -> Optional[Tensor]:
     """Regulariser -> tensor broadcastable to (..., N).  A float or a sequence
     of up to N floats is padded with its last value (reference docstring
@@ -181,11 +203,22 @@ def _as_diag(diag, n: int, dtype: torch.dtype, device: torch.device) -> Optional
         return None
     if torch.is_tensor(diag) and diag.dim() >= 1 and diag.shape[-1] in (1, n):
         return diag.to(device=device, dtype=dtype).expand(*diag.shape[:-1], n)
+    key = None
+    if isinstance(diag, (int, float)):
+        key = ((float(diag),), n, dtype, device)
+    elif isinstance(diag, (list, tuple)) and all(isinstance(x, (int, float)) for x in diag):
+        key = (tuple(float(x) for x in diag), n, dtype, device)
+    if key is not None and key in _REG_CACHE:
+        return _REG_CACHE[key]
     e = torch.as_tensor(diag, dtype=dtype).flatten()
     if len(e) > n or len(e) == 0:
         raise ValueError(f"regulariser has {len(e)} entries for a matrix of order {n}")
-    e = torch.cat([e, e[-1].expand(n - len(e))])
-    return e.to(device)
+    e = torch.cat([e, e[-1].expand(n - len(e))]).to(device)
+    if key is not None:
+        if len(_REG_CACHE) > 256:
+            _REG_CACHE.clear()
+        _REG_CACHE[key] = e
+    return e
 
 
 def sym_solve(mat: Tensor, vec: Tensor,
@@ -220,6 +253,26 @@ def sym_solve(mat: Tensor, vec: Tensor,
         if diag is not None:
             raise TypeError("give the regulariser as `diag` or as `eps`, not both")
         diag = eps
+    if (dtype is None and torch.is_tensor(mat) and torch.is_tensor(vec) and D.plain_cuda(vec, mat, out)
+            and (out is None or out.shape == vec.shape)):
+        # fast path: dense CUDA fields with the same batch dims
+        n = vec.shape[-1]
+        _check_n(n)
+        nn = mat.shape[-1]
+        layout = D.detect_layout(nn, n)
+        dev = vec.device
+        reg = _as_diag(diag, n, vec.dtype, dev)
+        if reg is None or reg.dim() == 1 or D.plain_cuda(vec, reg):
+            res = out if out is not None else torch.empty_like(vec)
+            nb = vec.numel() // n
+            if nb > 0:
+                with D.device_of(dev):
+                    rc = _lib.load().nfm_sym_solve(
+                        D.dtype_code(vec.dtype), n, layout, _algo(method), nb, mat.data_ptr(), nn, vec.data_ptr(), n,
+                        None if reg is None else reg.data_ptr(), 0 if reg is None or reg.dim() == 1 else n,
+                        res.data_ptr(), n, D.current_stream_ptr(dev))
+                _lib.check(rc, "nfm_sym_solve")
+            return res
     mat, vec = torch.as_tensor(mat), torch.as_tensor(vec)
     dev = D.common_device(mat, vec)
     cdt = D.compute_dtype(mat, vec, dtype=dtype)
@@ -264,7 +317,7 @@ def sym_solve(mat: Tensor, vec: Tensor,
         m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
         v = D.as_operand(vec, batch, 1, cdt, allow_estride=True)
         r = D.as_operand(reg, batch, 1, cdt, allow_estride=True) if reg is not None else None
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = _lib.load().nfm_sym_solve_ex(
                 code, n, layout, algo, nb, m.c_struct(), v.c_struct(), r.c_struct() if r is not None else None,
                 o.c_struct(), D.current_stream_ptr(dev))
@@ -305,6 +358,20 @@ def sym_invert(mat: Tensor, diag: bool = False, dtype: Optional[torch.dtype] = N
     -------
     imat : `(..., M or M*(M+1)//2) tensor` (compact storage, same ordering)
     """
+    if dtype is None and torch.is_tensor(mat) and D.plain_cuda(mat) and (
+            out is None or (D.plain_cuda(mat, out) and out.shape[-1] == (D.packed_order(mat.shape[-1]) if diag else mat.shape[-1]))):
+        nn = mat.shape[-1]
+        n = D.packed_order(nn)
+        _check_n(n)
+        no = n if diag else nn
+        res = out if out is not None else torch.empty((*mat.shape[:-1], no), dtype=mat.dtype, device=mat.device)
+        nb = mat.numel() // nn
+        if nb > 0:
+            with D.device_of(mat.device):
+                rc = _lib.load().nfm_sym_invert(D.dtype_code(mat.dtype), n, _algo(method), int(bool(diag)), nb,
+                                                mat.data_ptr(), nn, res.data_ptr(), no, D.current_stream_ptr(mat.device))
+            _lib.check(rc, "nfm_sym_invert")
+        return res
     mat = torch.as_tensor(mat)
     dev = mat.device
     cdt = D.compute_dtype(mat, dtype=dtype)
@@ -338,7 +405,7 @@ def sym_invert(mat: Tensor, diag: bool = False, dtype: Optional[torch.dtype] = N
     o, res, copy_back = D.out_operand(out, (*batch, no), 1, cdt, dev, allow_estride=True)
     if nb > 0:
         m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = _lib.load().nfm_sym_invert_ex(code, n, algo, int(bool(diag)), nb, m.c_struct(), o.c_struct(),
                                                D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_sym_invert")
@@ -370,7 +437,7 @@ def _unary(fn_name: str, x: Tensor, n: int, out_shape, rec_ndim_out: int) -> Ten
     o, res, _ = D.out_operand(None, tuple(out_shape), rec_ndim_out, cdt, dev)
     if nb > 0:
         m = D.as_operand(x, batch, 1, cdt)
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = getattr(_lib.load(), fn_name)(D.dtype_code(cdt), n, nb, m.ptr, m.stride, o.ptr, o.stride,
                                                D.current_stream_ptr(dev))
         _lib.check(rc, fn_name)
@@ -436,7 +503,7 @@ def sym_matmul(j: Tensor, h: Tensor) -> Tensor:
     if nb > 0:
         jo = D.as_operand(j, batch, 2, cdt)
         ho = D.as_operand(h, batch, 1, cdt)
-        with torch.cuda.device(dev):
+        with D.device_of(dev):
             rc = _lib.load().nfm_sym_matmul(D.dtype_code(cdt), k, d, mode, nb, jo.ptr, jo.stride, ho.ptr, ho.stride,
                                             o.ptr, o.stride, D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_sym_matmul")
