@@ -10,6 +10,7 @@ template <typename T, int ALGO> struct InvBind { template <int N> using Op = Bat
 template <typename T> struct DetBind { template <int N> using Op = BatchDetOp<T, N>; };
 template <typename T> struct MvBind { template <int N> using Op = BatchMatvecOp<T, N>; };
 template <typename T, int ALGO> struct SolBind { template <int N> using Op = BatchSolveOp<T, N, ALGO>; };
+template <typename T, int K, int ALGO> struct SolKBind { template <int N> using Op = BatchSolveKOp<T, N, K, ALGO>; };
 
 #if NFM_PART == 0
 template <typename T>
@@ -39,12 +40,36 @@ int batch_solve_lu_impl(int n, const KParams& p, cudaStream_t s) {
   return DispatchN<SolBind<T, NFM_ALGO_LU>::template Op, 1, NFM_MAX_N>::run(n, p, s);
 }
 template int batch_solve_lu_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
-#else
+#elif NFM_PART == 3
 template <typename T>
 int batch_solve_ldl_impl(int n, const KParams& p, cudaStream_t s) {
   return DispatchN<SolBind<T, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
 }
 template int batch_solve_ldl_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+#elif NFM_PART == 4
+// 2..4 right-hand sides, pivoted LU
+template <typename T>
+int batch_solvek_lu_impl(int n, int k, const KParams& p, cudaStream_t s) {
+  switch (k) {
+    case 2: return DispatchN<SolKBind<T, 2, NFM_ALGO_LU>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+    case 3: return DispatchN<SolKBind<T, 3, NFM_ALGO_LU>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+    case 4: return DispatchN<SolKBind<T, 4, NFM_ALGO_LU>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+  }
+  return NFM_E_UNSUPPORTED;
+}
+template int batch_solvek_lu_impl<NFM_SCALAR>(int, int, const KParams&, cudaStream_t);
+#else
+// 2..4 right-hand sides, LDL^T
+template <typename T>
+int batch_solvek_ldl_impl(int n, int k, const KParams& p, cudaStream_t s) {
+  switch (k) {
+    case 2: return DispatchN<SolKBind<T, 2, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+    case 3: return DispatchN<SolKBind<T, 3, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+    case 4: return DispatchN<SolKBind<T, 4, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+  }
+  return NFM_E_UNSUPPORTED;
+}
+template int batch_solvek_ldl_impl<NFM_SCALAR>(int, int, const KParams&, cudaStream_t);
 #endif
 
 }  // namespace nfm

@@ -120,6 +120,51 @@ struct BatchSolveOp {
   }
 };
 
+// X = A^-1 B with K right-hand sides; B and X are N x K row-major records
+template <typename T, int N, int K, int ALGO>
+struct BatchSolveKOp {
+  using scalar = T;
+  static constexpr int kLen0 = N * N;
+  static constexpr int kLen1 = N * K;
+  static constexpr int kLen2 = 1;
+  static constexpr int kUse = 3;
+  static constexpr int kOut = N * K;
+  static constexpr bool kHeavy = ALGO != NFM_ALGO_LDL && N >= 2;
+
+  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&b)[kLen1], const T (&)[1], int present,
+                                               int flags, T (&x)[kOut]) {
+    if constexpr (ALGO == NFM_ALGO_LDL) {
+      LDL<T, N> f;
+      ldl_from_dense_lower<T, N>(a, f);
+      f.factor();
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        T col[N], sol[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) col[i] = b[i * K + c];
+        f.solve(col, sol);
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i * K + c] = sol[i];
+      }
+    } else {
+      GaussPP<T, N, K> g;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) g.a[i][j] = a[i * N + j];
+#pragma unroll
+        for (int c = 0; c < K; ++c) g.b[i][c] = b[i * K + c];
+      }
+      g.eliminate();
+      g.back_substitute();
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int c = 0; c < K; ++c) x[i * K + c] = g.b[i][c];
+    }
+  }
+};
+
 template <typename T, int N>
 struct BatchMatvecOp {
   using scalar = T;

@@ -240,6 +240,17 @@ int nfm_batch_solve(int dtype, int n, int nrhs, int algo, int64_t batch, const v
   if (algo == NFM_ALGO_AUTO) algo = NFM_ALGO_LU;
   if (algo != NFM_ALGO_LU && algo != NFM_ALGO_LDL) return fail(NFM_E_UNSUPPORTED, "batch_solve: algo must be LU or LDL");
   auto s = static_cast<cudaStream_t>(stream);
+  if (nrhs >= 2 && nrhs <= 4) {  // register kernels through the TMA pipeline
+    Args a;
+    a.in(0, mat, a_stride, true);
+    a.in(1, b, b_stride, true);
+    a.out(out, out_stride);
+    if (a.rc) return a.rc;
+    a.p.batch = batch;
+    if (algo == NFM_ALGO_LDL)
+      return finish(dtype == NFM_F32 ? batch_solvek_ldl_impl<float>(n, nrhs, a.p, s) : batch_solvek_ldl_impl<double>(n, nrhs, a.p, s));
+    return finish(dtype == NFM_F32 ? batch_solvek_lu_impl<float>(n, nrhs, a.p, s) : batch_solvek_lu_impl<double>(n, nrhs, a.p, s));
+  }
   if (nrhs > 1) {
     if (mat == nullptr || b == nullptr || out == nullptr) return fail(NFM_E_BADARG, "NULL operand");
     if (a_stride < 0 || b_stride < 0 || out_stride < 0) return fail(NFM_E_BADARG, "negative batch stride");

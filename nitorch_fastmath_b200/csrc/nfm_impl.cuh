@@ -35,6 +35,9 @@ template <typename T> int batch_det_impl(int n, const KParams& p, cudaStream_t s
 template <typename T> int batch_matvec_impl(int n, const KParams& p, cudaStream_t s);
 template <typename T> int batch_solve_lu_impl(int n, const KParams& p, cudaStream_t s);
 template <typename T> int batch_solve_ldl_impl(int n, const KParams& p, cudaStream_t s);
+// parts 4 / 5: 2..4 right-hand sides (register kernels); more go to the run-time-sized kernel
+template <typename T> int batch_solvek_lu_impl(int n, int k, const KParams& p, cudaStream_t s);
+template <typename T> int batch_solvek_ldl_impl(int n, int k, const KParams& p, cudaStream_t s);
 
 // run-time-sized fallbacks (nfm_generic.cu)
 template <typename T>
