@@ -64,6 +64,7 @@ struct TileGeom {
   static constexpr int kBytesOut = bytes(Op::kOut);
   static constexpr int kFootOut = footprint(Op::kOut);
   static_assert(kTile % 64 == 0, "tile must be a multiple of 64 matrices");
+  static_assert(!SEG || (bytes(Op::kLen0) / kSegs) % 16 == 0, "segments must keep the 16 B alignment of bulk copies");
   static_assert(kBytes0 % 16 == 0 && kBytes1 % 16 == 0 && kBytes2 % 16 == 0 && kBytesOut % 16 == 0,
                 "tile byte counts must be multiples of 16 for TMA bulk copies");
 
@@ -325,8 +326,15 @@ struct TuneBase {
   // operand 2 is the optional one in every op that has it
   static constexpr int kInBytes = (((Op::kUse >> 0) & 1) * Op::kLen0 + ((Op::kUse >> 1) & 1) * Op::kLen1) * int(sizeof(T));
   static constexpr int kOutBytes = Op::kOut * int(sizeof(T));
-  // records that are a multiple of 32 B bank-conflict in the dense layout
-  static constexpr bool conflicts(int len) { return (len * int(sizeof(T))) % 32 == 0; }
+  // Records that are a multiple of 32 B bank-conflict in the dense layout:
+  // 2-way at 32 B, 4-way at 64 B, 8-way at 128 B.  The segmented layout removes
+  // that but its 8x smaller bulk copies cost ~7-15 %, so it is used when an
+  // operand conflicts >= 4-way, or 2-way on an operand that carries at least
+  // half of the traffic (a 2-way conflict on a small vector is cheaper).
+  static constexpr int rec_bytes(int len) { return len * int(sizeof(T)); }
+  static constexpr bool heavy(int len) { return rec_bytes(len) % 64 == 0; }
+  static constexpr bool light(int len) { return rec_bytes(len) % 32 == 0 && 2 * rec_bytes(len) >= kInBytes + kOutBytes; }
+  static constexpr bool conflicts(int len) { return heavy(len) || light(len); }
 #ifdef NFM_TUNE_SEG
   static constexpr bool kSeg = NFM_TUNE_SEG;
 #else
