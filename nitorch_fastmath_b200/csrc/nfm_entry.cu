@@ -2,6 +2,7 @@
 // block assembly, dispatch to the typed implementations.  No kernels here.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "nfm_impl.cuh"
 #include "nfm_pipeline.cuh"
@@ -34,6 +35,14 @@ const DeviceInfo& device_info() {
     ready[dev].store(1, std::memory_order_release);
   }
   return cache[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("NFM_DISABLE_PDL");
+    return !(v != nullptr && v[0] == '1');
+  }();
+  return on;
 }
 
 int current_device() {

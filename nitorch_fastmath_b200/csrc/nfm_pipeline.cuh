@@ -399,6 +399,8 @@ struct TuneFixed : TuneBase<Op> {
 template <class Op>
 struct Tune : TuneRule<Op> {};
 
+bool pdl_enabled();  // nfm_entry.cu: false when the environment has NFM_DISABLE_PDL=1
+
 // Launch with programmatic stream serialization: the kernel may become resident
 // while the previous kernel in the stream drains; it touches global memory only
 // after griddepcontrol.wait, so ordering is unchanged.
@@ -411,7 +413,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, si
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;  // NFM_DISABLE_PDL=1 turns it off
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);

@@ -23,6 +23,7 @@ const DeviceInfo& device_info() {
   return d;
 }
 int current_device() { return 0; }
+bool pdl_enabled() { return true; }
 }  // namespace nfm
 
 using namespace nfm;
