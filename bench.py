@@ -264,6 +264,17 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(kind, n, dtype, batch, steps=3, warmup=1, budget_s=20.0):
     """The reference's CPU algorithm (oracle port, torch CPU ops exactly as the
     reference issues them) on all host cores, on a bounded sample of the
@@ -290,7 +301,19 @@ def cpu_baseline(kind, n, dtype, batch, steps=3, warmup=1, budget_s=20.0):
         oracle_call(kind, ins)
         times.append(time.perf_counter() - t0)
     mean = sum(times) / len(times)
+    # one single-thread figure for context, on a slice of the sample
+    single = None
+    try:
+        small = [t[: min(sample, 1 << 21)] for t in ins]
+        torch.set_num_threads(1)
+        oracle_call(kind, small)
+        t0 = time.perf_counter()
+        oracle_call(kind, small)
+        single = small[0].shape[0] / (time.perf_counter() - t0)
+    finally:
+        torch.set_num_threads(cores)
     return {"value": sample / mean, "unit": "matrices/s", "cores": torch.get_num_threads(), "kind": "port",
+            "cpu_model": cpu_model(), "single_thread_value": single,
             "sample": f"{sample} of {batch} matrices per step, {steps} steps after {warmup} warm-up; "
                       "oracle/ref_port.py = the reference's torch-CPU algorithm",
             "best_value": sample / min(times), "seconds_per_step": mean, "sample_matrices": sample}
