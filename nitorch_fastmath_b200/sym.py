@@ -71,8 +71,8 @@ def _to_device_inputs(*tensors):
 
 def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
             dtype: Optional[torch.dtype], out: Optional[Tensor]) -> Tensor:
-    if (dtype is None and torch.is_tensor(mat) and torch.is_tensor(vec) and D.plain_cuda(vec, mat, inp, out)
-            and (out is None or out.shape == vec.shape)):
+    if (torch.is_tensor(mat) and torch.is_tensor(vec) and (dtype is None or dtype == vec.dtype)
+            and D.plain_cuda(vec, mat, inp, out) and (out is None or out.shape == vec.shape)):
         # fast path: dense CUDA fields with the same batch dims
         n = vec.shape[-1]
         _check_n(n)
@@ -253,8 +253,8 @@ def sym_solve(mat: Tensor, vec: Tensor,
         if diag is not None:
             raise TypeError("give the regulariser as `diag` or as `eps`, not both")
         diag = eps
-    if (dtype is None and torch.is_tensor(mat) and torch.is_tensor(vec) and D.plain_cuda(vec, mat, out)
-            and (out is None or out.shape == vec.shape)):
+    if (torch.is_tensor(mat) and torch.is_tensor(vec) and (dtype is None or dtype == vec.dtype)
+            and D.plain_cuda(vec, mat, out) and (out is None or out.shape == vec.shape)):
         # fast path: dense CUDA fields with the same batch dims
         n = vec.shape[-1]
         _check_n(n)
