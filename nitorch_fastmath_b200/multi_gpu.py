@@ -42,8 +42,8 @@ def _run(devices: Sequence[int], batch: int, work: Callable[[int, int], None]) -
     def job(rank: int) -> None:
         begin, end = shard_bounds(batch, world, rank)
         if end > begin:
-            torch.cuda.set_device(devices[rank])
-            work(begin, end)
+            with torch.cuda.device(devices[rank]):   # restored on exit: the caller's current device is untouched
+                work(begin, end)
 
     if world == 1:
         job(0)

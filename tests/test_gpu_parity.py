@@ -690,3 +690,25 @@ def test_sugar_surface(nfm):
         nfm.lmdiv(torch.zeros(3, 4, 5, device=DEV), torch.zeros(3, 4, 1, device=DEV))
     with pytest.raises(NotImplementedError):
         nfm.inv(torch.eye(3, device=DEV)[None], method="svd")
+
+
+def test_tensors_on_a_non_current_device(nfm):
+    """Operands on cuda:1 while cuda:0 is current: the call must run on the
+    tensors' device (needs a 2-GPU box; skipped otherwise)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    assert torch.cuda.current_device() == 0
+    d1 = torch.device("cuda:1")
+    for n in (3, 6):
+        mat = G.spd_packed(50_000, n, torch.float32, seed=n)
+        vec = G.vectors(50_000, n, torch.float32, seed=n + 1)
+        x = nfm.sym_solve(mat.to(d1), vec.to(d1))
+        assert x.device == d1
+        close(x, P.sym_solve(mat, vec), torch.float32)
+        close(nfm.sym_solve(mat.to(d1)[::2], vec.to(d1)[::2]), P.sym_solve(mat[::2], vec[::2]), torch.float32)
+        close(nfm.sym_invert(mat.to(d1)), P.sym_invert(mat), torch.float32)
+        a = G.dense_shifted(10_000, n, torch.float64, seed=n)
+        close(nfm.batchinv(a.to(d1)), P.batchinv(a), torch.float64, 2)
+    with pytest.raises(RuntimeError):
+        nfm.sym_solve(mat.to(d1), vec.to("cuda:0"))
+    assert torch.cuda.current_device() == 0
