@@ -41,6 +41,7 @@ __all__ = [
     "sym_solve", "sym_solve_ref_eps", "sym_invert",
     "batchdet", "batchinv", "batchmatvec", "closed_det", "closed_inv",
     "lmdiv", "solvevec", "inv",
+    "sym_outer", "sym_matmul", "sym_det",
 ]
 
 
@@ -317,6 +318,43 @@ def sym_invert(mat: Tensor, diag: bool = False) -> Tensor:
                 out[..., nxt] = col[..., j]
                 nxt += 1
     return out
+
+
+# --------------------------------------------------------------------------
+# "next" rows: outer product, J^T H J, determinant  (_impl/sym.py:496-670, :401-452)
+# --------------------------------------------------------------------------
+
+def sym_outer(x: Tensor) -> Tensor:
+    """x x^T in packed order (_impl/sym.py:496-528, the no-grad branch)."""
+    n = x.shape[-1]
+    return torch.stack([x[..., i] * x[..., j] for i, j in packed_order(n)], dim=-1)
+
+
+def sym_matmul(j: Tensor, h: Tensor) -> Tensor:
+    """What the reference's sym_matmul returns (_impl/sym.py:637-670).
+
+    Documented as J^T H J with j (..., k, d) and packed h (..., k(k+1)/2); the
+    general branch ``jhjn`` (:596-634) computes exactly that, but the unrolled
+    branches taken for k == d in {1, 2, 3} (``jhj1/2/3`` :532-593) index the
+    Jacobian the other way round and return J H J^T.  Restated as behaviour
+    (a dense congruence), not term by term: agreement with the reference is to
+    rounding (about 1e-15 in fp64), not bit for bit."""
+    k, d = j.shape[-2:]
+    hf = sym_to_full(h)
+    if k == d and k <= 3:
+        full = j @ hf @ j.transpose(-1, -2)
+    else:
+        full = j.transpose(-1, -2) @ hf @ j
+    return full_to_sym(full)
+
+
+def sym_det(mat: Tensor) -> Tensor:
+    """Determinant of a packed symmetric matrix.  The reference's sym_det
+    (_impl/sym.py:401-452) takes the matrix order from a *batch* dimension
+    (:434), so it raises or is wrong unless the batch size happens to equal
+    N(N+1)/2; this is the documented result, ``det(sym_to_full(mat))`` -- the
+    reference's own N > 4 branch (:449-450)."""
+    return torch.det(sym_to_full(mat))
 
 
 # --------------------------------------------------------------------------

@@ -97,6 +97,25 @@ def run(verbose: bool = True) -> int:
             check(f"closed_inv n={n} {tag}", P.closed_inv(a), inv_ref)
             check(f"closed_det n={n} {tag}", P.closed_det(a), det_ref)
 
+    # "next" rows: sym_outer bit for bit; sym_matmul restated as behaviour (dense
+    # congruence incl. the J H J^T quirk of the unrolled k == d <= 3 branches): to rounding
+    for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 1e-13)):
+        tag = "f32" if dtype == torch.float32 else "f64"
+        x = G.vectors((4, 9), 5, dtype, seed=3)
+        check(f"sym_outer {tag}", P.sym_outer(x), ref_sym.sym_outer(x))
+        for k, d in ((1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (5, 3)):
+            jac = G.vectors((4, 9, k), d, dtype, seed=10 * k + d)
+            h = G.spd_packed((4, 9), k, dtype, seed=k)
+            want = ref_sym.sym_matmul(jac, h)
+            check(f"sym_matmul k={k} d={d} {tag}", P.sym_matmul(jac, h), want, exact=False,
+                  tol=tol * float(want.abs().max()))
+        # sym_det is not compared: the reference takes the order from a batch dimension
+        # (_impl/sym.py:434), so it raises or is wrong unless the batch size happens to
+        # equal N(N+1)/2 -- e.g. N = 3 with a batch of exactly 6:
+        m3 = G.spd_packed(6, 3, dtype, seed=8)
+        check(f"sym_det n=3 batch=6 {tag}", P.sym_det(m3), ref_sym.sym_det(m3), exact=False,
+              tol=tol * float(P.sym_det(m3).abs().max()))
+
     if verbose:
         for name, d, ok in rows:
             if not ok or d != 0.0:

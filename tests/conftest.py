@@ -48,3 +48,8 @@ def sym_golden():
 @pytest.fixture(scope="session")
 def dense_golden():
     return Golden(os.path.join(GOLDEN, "dense_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def extra_golden():
+    return Golden(os.path.join(GOLDEN, "extra_golden.npz"))

@@ -84,9 +84,23 @@ def main():
                 fd = ref_bat.det2 if n == 2 else ref_bat.det3
                 dense[f"{k}_closed_inv"] = fi(c).movedim(0, -1).movedim(0, -1).contiguous().numpy()
                 dense[f"{k}_closed_det"] = fd(c).contiguous().numpy()
+    # "next" rows: sym_outer and sym_matmul straight from the reference
+    extra = {}
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        for n in (1, 2, 3, 5, 10):
+            x = G.vectors(BATCH, n, dtype, seed=11000 + n)
+            extra[f"{tag}_outer{n}_x"] = x.numpy()
+            extra[f"{tag}_outer{n}"] = ref_sym.sym_outer(x).numpy()
+        for k, d in ((1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1), (5, 3), (6, 6)):
+            jac = G.vectors((*BATCH, k), d, dtype, seed=12000 + 10 * k + d)
+            h = G.spd_packed(BATCH, k, dtype, seed=13000 + k)
+            extra[f"{tag}_jhj{k}x{d}_j"] = jac.numpy()
+            extra[f"{tag}_jhj{k}x{d}_h"] = h.numpy()
+            extra[f"{tag}_jhj{k}x{d}"] = ref_sym.sym_matmul(jac, h).contiguous().numpy()
+    np.savez_compressed(os.path.join(HERE, "extra_golden.npz"), **extra)
     np.savez_compressed(os.path.join(HERE, "sym_golden.npz"), **sym)
     np.savez_compressed(os.path.join(HERE, "dense_golden.npz"), **dense)
-    for f in ("sym_golden.npz", "dense_golden.npz"):
+    for f in ("sym_golden.npz", "dense_golden.npz", "extra_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -460,6 +460,18 @@ def test_singular_does_not_trap(nfm):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_next_rows_golden(nfm, extra_golden, dtype):
+    """sym_outer / sym_matmul against outputs of the real reference (incl. its
+    J H J^T behaviour for k == d <= 3)."""
+    t = TAGS[dtype]
+    for n in (1, 2, 3, 5, 10):
+        close(nfm.sym_outer(extra_golden(f"{t}_outer{n}_x", DEV)), extra_golden(f"{t}_outer{n}"), dtype)
+    for k, d in ((1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1), (5, 3), (6, 6)):
+        got = nfm.sym_matmul(extra_golden(f"{t}_jhj{k}x{d}_j", DEV), extra_golden(f"{t}_jhj{k}x{d}_h", DEV))
+        close(got, extra_golden(f"{t}_jhj{k}x{d}"), dtype)
+
+
 def test_sym_matmul(nfm):
     dtype = torch.float64
     for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1), (6, 6), (5, 3), (3, 7), (10, 10)]:

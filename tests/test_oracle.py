@@ -65,6 +65,16 @@ def test_dense_against_golden(dense_golden, dtype, n):
         _close(P.closed_det(a), dense_golden(f"{k}_closed_det"), dtype, 0)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_next_rows_against_golden(extra_golden, dtype):
+    t = TAGS[dtype]
+    for n in (1, 2, 3, 5, 10):
+        _close(P.sym_outer(extra_golden(f"{t}_outer{n}_x")), extra_golden(f"{t}_outer{n}"), dtype)
+    for k, d in ((1, 1), (2, 2), (3, 3), (4, 4), (2, 3), (4, 2), (3, 1), (5, 3), (6, 6)):
+        got = P.sym_matmul(extra_golden(f"{t}_jhj{k}x{d}_j"), extra_golden(f"{t}_jhj{k}x{d}_h"))
+        assert G.rel_err(got, extra_golden(f"{t}_jhj{k}x{d}")) <= (2e-6 if dtype == torch.float32 else 1e-14)
+
+
 def test_known_answers():
     """Analytic KATs (the reference ships none)."""
     # [[2,1],[1,2]] packed = [2,2,1]; inverse = 1/3 [[2,-1],[-1,2]]
