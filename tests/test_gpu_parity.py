@@ -724,3 +724,41 @@ def test_tensors_on_a_non_current_device(nfm):
     with pytest.raises(RuntimeError):
         nfm.sym_solve(mat.to(d1), vec.to("cuda:0"))
     assert torch.cuda.current_device() == 0
+
+
+def test_randomised_dense_shapes_and_views(nfm):
+    """40 seeded random cases for the dense routines: order, batch shape, dtype,
+    non-contiguous / broadcast operands -- against the oracle (LAPACK)."""
+    import random
+    rng = random.Random(4321)
+    for case in range(40):
+        n = rng.randint(1, 10)
+        dtype = rng.choice(DTYPES)
+        nb = rng.randint(1, 3)
+        batch = tuple(rng.choice([1, 2, 3, 7, 33]) for _ in range(nb))
+        if rng.random() < 0.25:
+            batch = (rng.choice([300, 1100, 2053]),)
+        a = G.dense_shifted(batch, n, dtype, seed=case)
+        b = G.vectors(batch, n, dtype, seed=500 + case)
+        da, db = a.to(DEV), b.to(DEV)
+        layout = rng.choice(["plain", "transposed_storage", "sliced", "offset"])
+        if layout == "transposed_storage":      # column-major storage viewed row-major
+            da = da.transpose(-1, -2).contiguous().transpose(-1, -2)
+        elif layout == "sliced":
+            wide = torch.zeros(*batch, n, 2 * n, device=DEV, dtype=dtype)
+            wide[..., ::2] = da
+            da = wide[..., ::2]
+        elif layout == "offset":
+            flat = torch.zeros(da.numel() + 1, device=DEV, dtype=dtype)
+            flat[1:] = da.reshape(-1)
+            da = flat[1:].view(da.shape)
+        close(nfm.batchinv(da), P.batchinv(a), dtype, 2)
+        close(nfm.batchdet(da), P.batchdet(a), dtype, 0)
+        close(nfm.solvevec(da, db), P.solvevec(a, b), dtype)
+        close(nfm.batchmatvec(da, db), P.batchmatvec(a, b), dtype)
+        # vector broadcast against the batch of matrices
+        close(nfm.batchmatvec(da, db.reshape(-1, n)[0]), P.batchmatvec(a, b.reshape(-1, n)[0]), dtype)
+        close(nfm.solvevec(da, db.reshape(-1, n)[0].expand(*batch, n)), P.solvevec(a, b.reshape(-1, n)[0].expand(*batch, n)), dtype)
+        k = rng.randint(2, 6)
+        rhs = G.vectors((*batch, n), k, dtype, seed=900 + case)
+        close(nfm.lmdiv(da, rhs.to(DEV)), P.lmdiv(a, rhs), dtype, 2)
