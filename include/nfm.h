@@ -189,6 +189,19 @@ int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch,
                    const void *hess, int64_t hess_stride,
                    void *out, int64_t out_stride, void *stream);
 
+/* Fused regularised solve + update (the chain
+ * sym_solve_ -> sym_submatvec_/sub_ of a Gauss-Newton / Levenberg-Marquardt
+ * iteration, names at sym.py:31-33):
+ *     out = x - alpha * (A + lam I)^-1 v
+ * mat: packed records of n(n+1)/2; vec, x, out: records of n; `out` may alias `x`.
+ * algo: NFM_ALGO_AUTO or NFM_ALGO_LDL.  No counterpart function in the reference. */
+int nfm_sym_solve_update(int dtype, int n, int algo, int64_t batch,
+                         const void *mat, int64_t mat_stride,
+                         const void *vec, int64_t vec_stride,
+                         const void *x, int64_t x_stride,
+                         double lam, double alpha,
+                         void *out, int64_t out_stride, void *stream);
+
 /* ---- host-buffer pipelines (end-to-end path) --------------------------- */
 
 /* Bytes of device workspace the host pipelines want for `chunk` matrices per

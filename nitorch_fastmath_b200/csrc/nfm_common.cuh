@@ -36,6 +36,8 @@ struct KParams {
   i64 batch;     // matrices handled by this launch
   int present;   // bit i set: input operand i is present
   int flags;     // op-specific
+  double scal0;  // op-specific scalars (ops that declare kScalars; e.g. the
+  double scal1;  //  damping and step length of the fused solve + update)
 };
 
 // ---------------------------------------------------------------------------

@@ -124,6 +124,8 @@ static int matmul_kd(int k, int d, int mode, const KParams& p, cudaStream_t s) {
   return NFM_E_UNSUPPORTED;
 }
 
+template <typename T, int ALGO> struct SolveUpdBind { template <int N> using Op = SymSolveUpdateOp<T, N, ALGO>; };
+
 template <typename T> struct SDetBind { template <int N> using Op = SymDetOp<T, N>; };
 template <typename T> struct SFullBind { template <int N> using Op = SymToFullOp<T, N>; };
 template <typename T> struct SOuterBind { template <int N> using Op = SymOuterOp<T, N>; };
@@ -187,6 +189,38 @@ int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch, const void*
   p.batch = batch;
   auto s = static_cast<cudaStream_t>(stream);
   return dtype == NFM_F32 ? matmul_kd<float>(k, d, mode, p, s) : matmul_kd<double>(k, d, mode, p, s);
+}
+
+int nfm_sym_solve_update(int dtype, int n, int algo, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,
+                         int64_t vec_stride, const void* x, int64_t x_stride, double lam, double alpha, void* out,
+                         int64_t out_stride, void* stream) {
+  if (dtype != NFM_F32 && dtype != NFM_F64) { set_error("dtype must be NFM_F32 or NFM_F64"); return NFM_E_UNSUPPORTED; }
+  if (n < 1 || n > NFM_MAX_N) { set_error("matrix order must be in 1..10"); return NFM_E_UNSUPPORTED; }
+  if (algo != NFM_ALGO_AUTO && algo != NFM_ALGO_LDL) { set_error("sym_solve_update: algo must be AUTO or LDL"); return NFM_E_UNSUPPORTED; }
+  if (batch < 0 || !mat || !vec || !x || !out || mat_stride < 0 || vec_stride < 0 || x_stride < 0 || out_stride < 0) {
+    set_error("bad argument");
+    return NFM_E_BADARG;
+  }
+  KParams p{};
+  p.in[0].ptr = mat;
+  p.in[0].stride = mat_stride;
+  p.in[1].ptr = vec;
+  p.in[1].stride = vec_stride;
+  p.in[2].ptr = x;
+  p.in[2].stride = x_stride;
+  p.present = 7;
+  p.out = out;
+  p.out_stride = out_stride;
+  p.batch = batch;
+  p.scal0 = lam;
+  p.scal1 = alpha;
+  auto s = static_cast<cudaStream_t>(stream);
+  if (algo == NFM_ALGO_LDL) {
+    return dtype == NFM_F32 ? DispatchN<SolveUpdBind<float, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s)
+                            : DispatchN<SolveUpdBind<double, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+  }
+  return dtype == NFM_F32 ? DispatchN<SolveUpdBind<float, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s)
+                          : DispatchN<SolveUpdBind<double, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s);
 }
 
 }  // extern "C"

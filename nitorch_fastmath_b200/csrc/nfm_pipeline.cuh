@@ -49,6 +49,19 @@ extern std::atomic<unsigned long long> g_launch_count;
 extern thread_local int t_last_path_tma;
 void set_error(const char* fmt, ...);
 
+// Ops that take the two scalar parameters of KParams declare `kScalars`.
+template <class Op, class = void>
+struct has_scalars : std::false_type {};
+template <class Op>
+struct has_scalars<Op, std::void_t<decltype(Op::kScalars)>> : std::true_type {};
+
+template <class Op, class R0, class R1, class R2, class O>
+__device__ __forceinline__ void apply_op(const KParams& p, const R0& r0, const R1& r1, const R2& r2, O& o) {
+  using T = typename Op::scalar;
+  if constexpr (has_scalars<Op>::value) Op::apply(r0, r1, r2, p.present, p.flags, T(p.scal0), T(p.scal1), o);
+  else Op::apply(r0, r1, r2, p.present, p.flags, o);
+}
+
 constexpr int kSegs = 8;     // segments per tile in the SEG layout
 constexpr int kSegPad = 16;  // bytes of skew per segment
 
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       T o[Op::kOut];
-      Op::apply(r0[j], r1[j], r2[j], p.present, p.flags, o);
+      apply_op<Op>(p, r0[j], r1[j], r2[j], o);
       store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(tid + j * THREADS)), o);
     }
     if (ragged) {
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(128) strided_kernel(const __grid_constant__ KP
     if (p.present & 1) load_record_scalar(g0 + b * p.in[0].stride, r0, elem_stride(p.in[0].estride));
     if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1, elem_stride(p.in[1].estride));
     if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2, elem_stride(p.in[2].estride));
-    Op::apply(r0, r1, r2, p.present, p.flags, o);
+    apply_op<Op>(p, r0, r1, r2, o);
     store_record_scalar(gout + b * p.out_stride, o, elem_stride(p.out_estride));
   }
 }

@@ -109,6 +109,45 @@ struct SymSolveOp {
   }
 };
 
+// Fused Gauss-Newton / Levenberg-Marquardt step:
+//   out = x - alpha * (A + lam I)^-1 v        in0 = mat (packed), in1 = v, in2 = x
+// i.e. sym_solve_ with a scalar regulariser followed by the update of the
+// parameter field, without the round trip of the step through HBM.
+template <typename T, int N, int ALGO>
+struct SymSolveUpdateOp {
+  using scalar = T;
+  static constexpr int kLen0 = packed_len(N);
+  static constexpr int kLen1 = N;
+  static constexpr int kLen2 = N;
+  static constexpr int kUse = 7;
+  static constexpr int kOut = N;
+  static constexpr bool kHeavy = false;
+  static constexpr bool kScalars = true;
+
+  __device__ static __forceinline__ void apply(const T (&m_in)[kLen0], const T (&v)[N], const T (&x0)[N], int present,
+                                               int flags, T lam, T alpha, T (&out)[N]) {
+    T m[kLen0];
+#pragma unroll
+    for (int k = 0; k < kLen0; ++k) m[k] = (k < N) ? m_in[k] + lam : m_in[k];
+    T step[N];
+    if constexpr (N <= 4) {
+      sym_solve_closed<T, N>(m, v, step);
+    } else if constexpr (ALGO == NFM_ALGO_LDL) {
+      LDL<T, N> f;
+      f.load_packed(m);
+      f.factor();
+      f.solve(v, step);
+    } else {
+      LDL<T, N> f;
+      f.load_packed(m);
+      if (f.factor_checked()) f.solve(v, step);
+      else sym_solve_lu<T, N>(m, v, step);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = x0[i] - alpha * step[i];
+  }
+};
+
 // out = A^-1 (packed) or diag(A^-1)        in0 = mat
 template <typename T, int N, int ALGO, bool DIAG_ONLY>
 struct SymInvertOp {

@@ -39,6 +39,7 @@ __all__ = [
     'sym_submatvec', 'sym_submatvec_',
     'sym_solve', 'sym_solve_',
     'sym_invert', 'sym_invert_',
+    'sym_solve_update', 'sym_solve_update_',     # extension (not in the reference)
 ]
 
 _METHODS = {None: _lib.ALGO_AUTO, 'auto': _lib.ALGO_AUTO, 'ldl': _lib.ALGO_LDL, 'chol': _lib.ALGO_LDL,
@@ -336,6 +337,54 @@ def sym_solve_(mat: Tensor, vec: Tensor, diag=None, dtype: Optional[torch.dtype]
                eps=None, method: Optional[str] = None) -> Tensor:
     r"""In-place ``vec <- mat \ vec``; returns ``vec``  (reference name sym.py:33)."""
     return sym_solve(mat, vec, diag, dtype=dtype, out=vec, eps=eps, method=method)
+
+
+# ---------------------------------------------------------------------------
+# fused solve + update (extension; SURVEY.md section 8f rank 4)
+# ---------------------------------------------------------------------------
+
+def sym_solve_update(x: Tensor, mat: Tensor, vec: Tensor, lam: float = 0.0, alpha: float = 1.0,
+                     out: Optional[Tensor] = None, *, method: Optional[str] = None) -> Tensor:
+    r"""``x - alpha * (mat + lam*I) \ vec`` in one pass over HBM.
+
+    The Gauss-Newton / Levenberg-Marquardt update that otherwise is the chain
+    ``step = sym_solve(mat, vec, lam); x - alpha * step`` (reference names
+    sym.py:31-33); not a function of the reference.  CUDA tensors only;
+    ``mat (..., M*(M+1)//2)``, ``vec`` and ``x`` ``(..., M)`` with the same batch dims.
+    """
+    x, mat, vec = torch.as_tensor(x), torch.as_tensor(mat), torch.as_tensor(vec)
+    dev = D.common_device(x, mat, vec)
+    if dev.type != "cuda":
+        raise RuntimeError("sym_solve_update takes CUDA tensors")
+    n = vec.shape[-1]
+    _check_n(n)
+    if mat.shape[-1] != n * (n + 1) // 2 or x.shape[-1] != n:
+        raise ValueError("sym_solve_update takes a packed symmetric mat and x, vec of the same trailing size")
+    cdt = D.compute_dtype(x, mat, vec)
+    algo = _algo(method)
+    if algo not in (_lib.ALGO_AUTO, _lib.ALGO_LDL):
+        raise ValueError("sym_solve_update supports method 'auto' or 'ldl'")
+    batch = tuple(torch.broadcast_shapes(x.shape[:-1], mat.shape[:-1], vec.shape[:-1]))
+    nb = D.batch_count(batch)
+    o, res, copy_back = D.out_operand(out, (*batch, n), 1, cdt, dev)
+    if nb > 0:
+        m = D.as_operand(mat, batch, 1, cdt)
+        v = D.as_operand(vec, batch, 1, cdt)
+        xo = D.as_operand(x, batch, 1, cdt)
+        with D.device_of(dev):
+            rc = _lib.load().nfm_sym_solve_update(D.dtype_code(cdt), n, algo, nb, m.ptr, m.stride, v.ptr, v.stride,
+                                                  xo.ptr, xo.stride, float(lam), float(alpha), o.ptr, o.stride,
+                                                  D.current_stream_ptr(dev))
+        _lib.check(rc, "nfm_sym_solve_update")
+    if copy_back:
+        res.copy_(o.tensor)
+    return res
+
+
+def sym_solve_update_(x: Tensor, mat: Tensor, vec: Tensor, lam: float = 0.0, alpha: float = 1.0, *,
+                      method: Optional[str] = None) -> Tensor:
+    r"""In-place ``x -= alpha * (mat + lam*I) \ vec``; returns ``x``."""
+    return sym_solve_update(x, mat, vec, lam, alpha, out=x, method=method)
 
 
 # ---------------------------------------------------------------------------

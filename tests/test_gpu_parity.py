@@ -793,3 +793,24 @@ def test_accuracy_tracks_the_reference_on_ill_conditioned_spd(nfm, n):
     # fp64 on the same matrices stays at rounding level
     e64 = _per_matrix_err(nfm.sym_solve(mat64.to(DEV), vec64.to(DEV)), truth)
     assert e64.max() < 1e-9
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 6, 10])
+def test_fused_solve_update(nfm, dtype, n):
+    """x - alpha (A + lam I)^-1 v in one pass == the chain sym_solve -> update (oracle)."""
+    batch = 30_011
+    mat = G.spd_packed(batch, n, dtype, seed=n)
+    vec = G.vectors(batch, n, dtype, seed=n + 1)
+    x = G.vectors(batch, n, dtype, seed=n + 2)
+    for lam, alpha in ((0.0, 1.0), (0.3, 0.5)):
+        step = P.sym_solve(mat, vec, lam if lam else None)
+        want = x - alpha * step
+        got = nfm.sym_solve_update(x.to(DEV), mat.to(DEV), vec.to(DEV), lam, alpha)
+        num = (got.cpu().double() - want.double()).norm(dim=-1)
+        den = (x.double().norm(dim=-1) + alpha * step.double().norm(dim=-1)).clamp_min(1e-300)
+        assert float((num / den).max()) <= TOL[dtype]
+    xd = x.to(DEV)
+    assert nfm.sym_solve_update_(xd, mat.to(DEV), vec.to(DEV), 0.3, 0.5).data_ptr() == xd.data_ptr()
+    num = (xd.cpu().double() - want.double()).norm(dim=-1)
+    assert float((num / den).max()) <= TOL[dtype]
