@@ -64,3 +64,14 @@ def test_argument_validation_without_a_gpu():
     assert lib.nfm_sym_matmul(_lib.F32, 11, 3, 0, 4, p, 33, p, 66, p, 6, None) == -1
     with pytest.raises(_lib.NfmError):
         _lib.check(-2, "demo")
+
+
+def test_header_is_plain_c():
+    """include/nfm.h is a C ABI: it must compile as C99 without torch / CUDA headers."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr.strip() == "", r.stderr
