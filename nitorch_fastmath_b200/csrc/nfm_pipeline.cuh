@@ -412,6 +412,18 @@ struct TuneFixed : TuneBase<Op> {
 template <class Op>
 struct Tune : TuneRule<Op> {};
 
+// Second, smaller geometry for light ops with small records when a launch has
+// only a few tiles per CTA (mid-size batches: a multi-GPU slab, config 1).
+// Measured for the 3x3 fp32 solve (tune_main "small"): 512-matrix tiles beat
+// 1024 by 10 / 6 / 3.5 % at 0.5M / 1M / 2M matrices and lose by 3 % at 4M.
+template <class Op>
+struct TuneSmall {
+  using B = TuneBase<Op>;
+  static constexpr bool kEnabled = !Op::kHeavy && (B::kInBytes + B::kOutBytes <= 64) && Tune<Op>::kTile >= 1024;
+  static constexpr int kThreads = 256, kMpt = 2, kStages = 3;
+  static constexpr int kTilesPerCtaBelow = 20;  // use it when the big geometry would give fewer tiles per SM than this
+};
+
 bool pdl_enabled();  // nfm_entry.cu: false when the environment has NFM_DISABLE_PDL=1
 
 // Launch with programmatic stream serialization: the kernel may become resident
@@ -508,7 +520,16 @@ int run_op(KParams p, cudaStream_t stream) {
   if (fast && nstaged == 0) fast = false;
   if (fast) {
     // full tiles by TMA, the ragged remainder inside the same launch
-    int rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, p.batch / TILE, stream);
+    int rc;
+    bool small = false;
+    if constexpr (TuneSmall<Op>::kEnabled) small = p.batch / TILE < i64(TuneSmall<Op>::kTilesPerCtaBelow) * device_info().sm_count;
+    if constexpr (TuneSmall<Op>::kEnabled) {
+      using Ts = TuneSmall<Op>;
+      rc = small ? launch_tile<Op, Ts::kThreads, Ts::kMpt, Ts::kStages, Tn::kSeg>(p, p.batch / (Ts::kThreads * Ts::kMpt), stream)
+                 : launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, p.batch / TILE, stream);
+    } else {
+      rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, p.batch / TILE, stream);
+    }
     if (rc == 0) {
       t_last_path_tma = 1;
       return NFM_OK;

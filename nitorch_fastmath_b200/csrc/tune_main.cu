@@ -85,6 +85,47 @@ void run_config(const char* name, const Buffers& b, int alg_bytes) {
   fflush(stdout);
 }
 
+// small-batch variant: the big buffers are cut into `slices` sub-batches that are
+// visited round-robin, so that consecutive launches never find their data in L2
+template <class Op, int THREADS, int MPT, int STAGES, bool SEG>
+void run_sliced(const char* name, const Buffers& b, int alg_bytes, i64 sub) {
+  using T = typename Op::scalar;
+  const int slices = int(b.batch / sub);
+  std::vector<KParams> ps(slices);
+  for (int s = 0; s < slices; ++s) {
+    KParams p{};
+    p.in[0].ptr = static_cast<const T*>(b.in0) + i64(s) * sub * Op::kLen0;
+    p.in[0].stride = Op::kLen0;
+    p.present = 1;
+    if (Op::kUse & 2) {
+      p.in[1].ptr = static_cast<const T*>(b.in1) + i64(s) * sub * Op::kLen1;
+      p.in[1].stride = Op::kLen1;
+      p.present |= 2;
+    }
+    p.out = static_cast<T*>(b.out) + i64(s) * sub * Op::kOut;
+    p.out_stride = Op::kOut;
+    p.batch = sub;
+    ps[s] = p;
+  }
+  constexpr int TILE = THREADS * MPT;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < slices; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i], sub / TILE, 0);
+  cudaDeviceSynchronize();
+  const int reps = 10 * slices;
+  cudaEventRecord(e0);
+  for (int i = 0; i < reps; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i % slices], sub / TILE, 0);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double us = ms * 1e3 / reps;
+  printf("%-18s batch %8lld T=%4d thr=%3d st=%d : %7.2f us  %7.1f GB/s\n", name, sub, TILE, THREADS, STAGES, us,
+         double(sub) * alg_bytes / (us * 1e-6) / 1e9);
+  fflush(stdout);
+}
+
 template <typename T>
 Buffers make(i64 batch, int len0, int ndiag0, int len1, int lout) {
   Buffers b{};
@@ -121,6 +162,19 @@ int main(int argc, char** argv) {
     CFG(Op, "sym_solve3", 256, 2, 3, false, 48);
     CFG(Op, "sym_solve3", 256, 4, 4, false, 48);
     CFG(Op, "sym_solve3", 1024, 1, 3, false, 48);
+    release(buf);
+  }
+  if (want("small")) {
+    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
+    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
+    for (i64 sub : {i64(1) << 19, i64(1) << 20, i64(1) << 21, i64(1) << 22}) {
+      run_sliced<Op, 512, 2, 3, false>("solve3", buf, 48, sub);
+      run_sliced<Op, 256, 2, 3, false>("solve3", buf, 48, sub);
+      run_sliced<Op, 512, 1, 3, false>("solve3", buf, 48, sub);
+      run_sliced<Op, 256, 1, 4, false>("solve3", buf, 48, sub);
+      run_sliced<Op, 128, 2, 4, false>("solve3", buf, 48, sub);
+      run_sliced<Op, 256, 1, 3, false>("solve3", buf, 48, sub);
+    }
     release(buf);
   }
   if (want("solve6")) {
