@@ -61,6 +61,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// CTA-scope release / acquire on a shared-memory word (buffer hand-over in pool_kernel)
+__device__ __forceinline__ void st_release_shared(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -101,6 +115,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
   }
+}
+
+// L2 prefetch of a contiguous range (16-byte aligned, bytes % 16 == 0).  No
+// architectural effect: it only warms L2, the point of coherence, so it may be
+// issued BEFORE griddepcontrol.wait -- if the previous kernel still writes these
+// lines, the later real load sees the written data.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // 1-D TMA: shared -> global, tracked by the bulk async-group of the issuing thread.
@@ -146,6 +168,12 @@ __device__ __forceinline__ void static_for_down(F&& f) {
     static_for_down<B, E - 1>(f);
   }
 }
+
+// true if `pred` holds for any lane currently executing with this one.  The
+// pivoted eliminations use it to skip the predicated row / column exchanges of a
+// step in which no matrix of the warp pivots (always, on diagonally dominant or
+// SPD input); correctness does not depend on which lanes take part.
+__device__ __forceinline__ bool warp_any(bool pred) { return __any_sync(__activemask(), pred) != 0; }
 
 // programmatic dependent launch (PDL)
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

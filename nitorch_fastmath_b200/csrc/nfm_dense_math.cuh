@@ -94,16 +94,18 @@ struct GaussJordan {
         }
       });
       piv[k] = p;
-      static_for<k + 1, N>([&](auto I) {
-        constexpr int i = I;
-        const bool sw = (p == i);
-        static_for<0, N>([&](auto J) {
-          constexpr int j = J;
-          const T lo = a[k][j], hi = a[i][j];
-          a[k][j] = sw ? hi : lo;
-          a[i][j] = sw ? lo : hi;
+      if (warp_any(p != k)) {  // skipped when no matrix of the warp exchanges rows in this step
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const bool sw = (p == i);
+          static_for<0, N>([&](auto J) {
+            constexpr int j = J;
+            const T lo = a[k][j], hi = a[i][j];
+            a[k][j] = sw ? hi : lo;
+            a[i][j] = sw ? lo : hi;
+          });
         });
-      });
+      }
       const T rp = T(1) / a[k][k];
       a[k][k] = T(1);
       static_for<0, N>([&](auto J) { a[k][J] *= rp; });
@@ -122,16 +124,18 @@ struct GaussJordan {
     // (P A)^-1 = A^-1 P^T  ->  undo with column swaps in reverse order
     static_for_down<0, N>([&](auto K) {
       constexpr int k = K;
-      static_for<k + 1, N>([&](auto C) {
-        constexpr int c = C;
-        const bool sw = (piv[k] == c);
-        static_for<0, N>([&](auto I) {
-          constexpr int i = I;
-          const T lo = a[i][k], hi = a[i][c];
-          a[i][k] = sw ? hi : lo;
-          a[i][c] = sw ? lo : hi;
+      if (warp_any(piv[k] != k)) {
+        static_for<k + 1, N>([&](auto C) {
+          constexpr int c = C;
+          const bool sw = (piv[k] == c);
+          static_for<0, N>([&](auto I) {
+            constexpr int i = I;
+            const T lo = a[i][k], hi = a[i][c];
+            a[i][k] = sw ? hi : lo;
+            a[i][c] = sw ? lo : hi;
+          });
         });
-      });
+      }
     });
   }
 };

@@ -45,6 +45,14 @@ bool pdl_enabled() {
   return on;
 }
 
+bool balance_enabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("NFM_DISABLE_BALANCE");
+    return !(v != nullptr && v[0] == '1');
+  }();
+  return on;
+}
+
 int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);

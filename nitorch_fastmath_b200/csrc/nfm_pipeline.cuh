@@ -64,28 +64,37 @@ __device__ __forceinline__ void apply_op(const KParams& p, const R0& r0, const R
 
 constexpr int kSegs = 8;     // segments per tile in the SEG layout
 constexpr int kSegPad = 16;  // bytes of skew per segment
+// The number of matrices in a tile is a run-time value (so that a launch can be
+// cut into equal tiles, see balanced_tile()); it is a multiple of kTileGran, which
+// keeps every operand tile -- and every one of the 8 segments of the SEG layout --
+// a multiple of 16 bytes for any record length (records are multiples of 4 bytes).
+constexpr int kTileGran = 32;
 
 template <class Op, int THREADS, int MPT, bool SEG>
 struct TileGeom {
   using T = typename Op::scalar;
   static constexpr int kTile = THREADS * MPT;
   static constexpr int kPad = SEG ? kSegs * kSegPad : 0;
+  // matrices whose records make up a multiple of 16 bytes for every record
+  // length (records are multiples of 4 bytes); times 8 when the tile is segmented
+  static constexpr int kGran = SEG ? 4 * kSegs : 4;
   // payload bytes of one operand tile / its footprint in shared memory
   static constexpr int bytes(int len) { return kTile * len * int(sizeof(T)); }
   static constexpr int footprint(int len) { return bytes(len) + kPad; }
   static constexpr int kBytes0 = bytes(Op::kLen0), kBytes1 = bytes(Op::kLen1), kBytes2 = bytes(Op::kLen2);
   static constexpr int kBytesOut = bytes(Op::kOut);
   static constexpr int kFootOut = footprint(Op::kOut);
-  static_assert(kTile % 64 == 0, "tile must be a multiple of 64 matrices");
+  static_assert(kTile % kTileGran == 0, "tile capacity must be a multiple of kTileGran matrices");
   static_assert(!SEG || (bytes(Op::kLen0) / kSegs) % 16 == 0, "segments must keep the 16 B alignment of bulk copies");
   static_assert(kBytes0 % 16 == 0 && kBytes1 % 16 == 0 && kBytes2 % 16 == 0 && kBytesOut % 16 == 0,
                 "tile byte counts must be multiples of 16 for TMA bulk copies");
 
-  // byte offset of record m (0 <= m < kTile, in thread order) inside an operand tile
+  // byte offset of record m (0 <= m < tile_m, in thread order) inside an operand
+  // tile that holds tile_m <= kTile matrices (tile_m % kTileGran == 0)
   template <int LEN>
-  __device__ static __forceinline__ int rec_offset(int m) {
+  __device__ static __forceinline__ int rec_offset(int m, int tile_m) {
     if constexpr (SEG) {
-      constexpr int seg_bytes = bytes(LEN) / kSegs;
+      const int seg_bytes = (tile_m >> 3) * LEN * int(sizeof(T));
       return (m & (kSegs - 1)) * (seg_bytes + kSegPad) + (m >> 3) * LEN * int(sizeof(T));
     } else {
       return m * LEN * int(sizeof(T));
@@ -105,10 +114,10 @@ __host__ __device__ inline int staged_mask(const KParams& p) {
 
 // element e (0 <= e < count*LEN, tile-global order) -> byte offset in the staged tile
 template <class G, int LEN>
-__device__ __forceinline__ int elem_offset(int e) {
+__device__ __forceinline__ int elem_offset(int e, int tile_m) {
   using T = typename G::T;
   if constexpr (G::kPad != 0) {
-    constexpr int per_seg = G::kTile / kSegs * LEN;  // elements per segment
+    const int per_seg = (tile_m >> 3) * LEN;  // elements per segment
     const int seg = e / per_seg;
     return seg * (per_seg * int(sizeof(T)) + kSegPad) + (e - seg * per_seg) * int(sizeof(T));
   } else {
@@ -116,52 +125,96 @@ __device__ __forceinline__ int elem_offset(int e) {
   }
 }
 
-// ragged last tile: all threads copy `count` records between global memory and
-// the staged layout with plain coalesced accesses
+// ragged last tile: the `step` threads idx = 0..step-1 (a CTA or one warp) copy
+// `count` records between global memory and the staged layout with plain
+// coalesced accesses
 template <class G, int LEN>
-__device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typename G::T* src, int count) {
+__device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typename G::T* src, int count, int tile_m, int idx,
+                                          int step) {
   using T = typename G::T;
   constexpr int U = 4;  // independent loads in flight per thread
-  const int total = count * LEN, step = int(blockDim.x);
-  for (int e0 = threadIdx.x; e0 < total; e0 += U * step) {
+  const int total = count * LEN;
+  for (int e0 = idx; e0 < total; e0 += U * step) {
     T v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) v[u] = (e0 + u * step < total) ? src[e0 + u * step] : T(0);
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (e0 + u * step < total) *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e0 + u * step)) = v[u];
+      if (e0 + u * step < total) *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e0 + u * step, tile_m)) = v[u];
   }
 }
 
 template <class G, int LEN>
-__device__ __forceinline__ void coop_store(typename G::T* dst, const unsigned char* smem_tile, int count) {
+__device__ __forceinline__ void coop_store(typename G::T* dst, const unsigned char* smem_tile, int count, int tile_m, int idx,
+                                           int step) {
   using T = typename G::T;
   const int total = count * LEN;
-  for (int e = threadIdx.x; e < total; e += blockDim.x)
-    dst[e] = *reinterpret_cast<const T*>(smem_tile + elem_offset<G, LEN>(e));
+  for (int e = idx; e < total; e += step) dst[e] = *reinterpret_cast<const T*>(smem_tile + elem_offset<G, LEN>(e, tile_m));
 }
 
+#ifdef NFM_TIMELINE
+// development aid (tune_main.cu "timeline"): per-CTA %globaltimer stamps, row = launch id
+// (passed in KParams::scal1) * 1024 + CTA; grids of at most 1024 CTAs
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define NFM_STAMP(k)                                                                    \
+  do {                                                                                  \
+    if (threadIdx.x == 0 && g_timeline != nullptr)                                     \
+      g_timeline[(size_t(p.scal1) * 1024 + blockIdx.x) * 8 + (k)] = global_ns();          \
+  } while (0)
+#define NFM_STAMP_VAL(k, v)                                                             \
+  do {                                                                                  \
+    if (threadIdx.x == 0 && g_timeline != nullptr)                                     \
+      g_timeline[(size_t(p.scal1) * 1024 + blockIdx.x) * 8 + (k)] = (unsigned long long)(v); \
+  } while (0)
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+#else
+#define NFM_STAMP(k) \
+  do {               \
+  } while (0)
+#define NFM_STAMP_VAL(k, v) \
+  do {                      \
+  } while (0)
+#endif
+
 template <class Op, int THREADS, int MPT, int STAGES, bool SEG>
-__global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ KParams p, const i64 ntiles) {
-  // ntiles = number of FULL tiles (moved by TMA).  A ragged last tile of
-  // rem = p.batch - ntiles*TILE matrices is handled by the CTA whose turn it
-  // is, with a cooperative guarded copy in place of the bulk copies.
+__global__ void __launch_bounds__(THREADS)
+    tile_kernel(const __grid_constant__ KParams p, const i64 ntiles, const int tile_m, const int part_m) {
+  // The launch covers p.batch matrices as
+  //   ntiles tiles of tile_m <= THREADS*MPT matrices (tile_m % kTileGran == 0),
+  //   one partial tile of part_m < tile_m matrices (part_m % TileGeom::kGran == 0,
+  //     so it still moves by TMA, just with a smaller byte count), and
+  //   tail = p.batch - ntiles*tile_m - part_m < kGran matrices that cannot keep the
+  //     16-byte granularity of bulk copies: the last CTA does them straight from
+  //     global memory while its first tiles are in flight.
   using T = typename Op::scalar;
   using G = TileGeom<Op, THREADS, MPT, SEG>;
-  constexpr int TILE = G::kTile;
-  const int rem = int(p.batch - ntiles * TILE);
-  const i64 ntiles_all = ntiles + (rem > 0 ? 1 : 0);
+  NFM_STAMP(0);
+  const i64 ntiles_all = ntiles + (part_m > 0 ? 1 : 0);
+  const int tail = int(p.batch - ntiles * tile_m - part_m);
   constexpr int kIssuers = SEG ? kSegs : 1;  // threads that issue bulk copies (one segment each)
+  constexpr int nseg = SEG ? kSegs : 1;
+  constexpr int pad = SEG ? kSegPad : 0;
+  constexpr int es = int(sizeof(T));
   // L2 evict_first on the loads only for ops that write at least as much as they read
   constexpr bool kHint = Op::kOut >= ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0);
 
   extern __shared__ __align__(128) unsigned char smem[];
   const int staged = staged_mask(p);
+  // shared-memory footprints are sized for the full THREADS*MPT capacity
   const int f0 = (staged & 1) ? G::footprint(Op::kLen0) : 0;
   const int f1 = (staged & 2) ? G::footprint(Op::kLen1) : 0;
   const int f2 = (staged & 4) ? G::footprint(Op::kLen2) : 0;
   const int stage_bytes = f0 + f1 + f2;
-  const uint32_t tx_bytes = ((staged & 1) ? G::kBytes0 : 0) + ((staged & 2) ? G::kBytes1 : 0) + ((staged & 4) ? G::kBytes2 : 0);
+  const int staged_len = ((staged & 1) ? Op::kLen0 : 0) + ((staged & 2) ? Op::kLen1 : 0) + ((staged & 4) ? Op::kLen2 : 0);
 
   unsigned char* const in_base = smem;
   unsigned char* const out_base = smem + STAGES * stage_bytes;
@@ -172,6 +225,8 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
   const T* const g1 = static_cast<const T*>(p.in[1].ptr);
   const T* const g2 = static_cast<const T*>(p.in[2].ptr);
   T* const gout = static_cast<T*>(p.out);
+  // matrices in tile t
+  auto count_of = [&](i64 t) { return t < ntiles ? tile_m : part_m; };
 
   uint64_t policy = 0;
   if (tid == 0) {
@@ -180,34 +235,52 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
     fence_mbar_init();
   }
   if (tid < kIssuers) policy = policy_evict_first();
+#ifndef NFM_NO_PREFETCH
+  // Warm L2 with this CTA's first tiles while the previous kernel in the stream
+  // drains: under programmatic dependent launch this CTA becomes resident 1-3 us
+  // before griddepcontrol.wait releases it (profiles/r2_launch_timeline.txt), and
+  // HBM is under-used during that tail.  An L2 prefetch has no architectural
+  // effect, so it is safe ahead of the wait.
+  if (tid < STAGES) {
+    const i64 t = i64(blockIdx.x) + i64(tid) * gridDim.x;
+    if (t < ntiles_all) {
+      const i64 first = t * tile_m;
+      const uint32_t c = uint32_t(count_of(t));
+      if (staged & 1) bulk_prefetch_l2(g0 + first * Op::kLen0, c * Op::kLen0 * es);
+      if (staged & 2) bulk_prefetch_l2(g1 + first * Op::kLen1, c * Op::kLen1 * es);
+      if (staged & 4) bulk_prefetch_l2(g2 + first * Op::kLen2, c * Op::kLen2 * es);
+    }
+  }
+#endif
   __syncthreads();
   // programmatic dependent launch: everything above overlapped the previous
   // kernel's tail; its results are visible only after this wait
   grid_dependency_wait();
   grid_launch_dependents();
+  NFM_STAMP(1);
 
   // producer (threads 0..kIssuers-1): thread 0 arms the stage barrier with the
   // tile's byte count; each issuer sends its segment of every staged operand
   auto issue = [&](int stage, i64 tile) {
     unsigned char* dst = in_base + stage * stage_bytes;
-    const i64 first = tile * TILE;
-    if (tid == 0) mbar_arrive_expect_tx(&full[stage], tx_bytes);
-    constexpr int nseg = SEG ? kSegs : 1;
+    const i64 first = tile * tile_m;
+    const int per_seg = count_of(tile) / nseg;  // matrices per segment (per tile when !SEG)
+    if (tid == 0) mbar_arrive_expect_tx(&full[stage], uint32_t(per_seg * nseg * staged_len * es));
     const int seg = SEG ? tid : 0;
     if (staged & 1) {
-      constexpr int sb = G::kBytes0 / nseg;
-      bulk_g2s<kHint>(dst + seg * (sb + (SEG ? kSegPad : 0)), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb,
-               sb, &full[stage], policy);
+      const int sb = per_seg * Op::kLen0 * es;
+      bulk_g2s<kHint>(dst + seg * (sb + pad), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb, sb,
+                      &full[stage], policy);
     }
     if (staged & 2) {
-      constexpr int sb = G::kBytes1 / nseg;
-      bulk_g2s<kHint>(dst + f0 + seg * (sb + (SEG ? kSegPad : 0)),
-               reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb, sb, &full[stage], policy);
+      const int sb = per_seg * Op::kLen1 * es;
+      bulk_g2s<kHint>(dst + f0 + seg * (sb + pad), reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb, sb,
+                      &full[stage], policy);
     }
     if (staged & 4) {
-      constexpr int sb = G::kBytes2 / nseg;
-      bulk_g2s<kHint>(dst + f0 + f1 + seg * (sb + (SEG ? kSegPad : 0)),
-               reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb, sb, &full[stage], policy);
+      const int sb = per_seg * Op::kLen2 * es;
+      bulk_g2s<kHint>(dst + f0 + f1 + seg * (sb + pad), reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb,
+                      sb, &full[stage], policy);
     }
   };
 
@@ -215,8 +288,22 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       const i64 t = i64(blockIdx.x) + i64(s) * gridDim.x;
-      if (t < ntiles) issue(s, t);
+      if (t < ntiles_all) issue(s, t);
     }
+  }
+
+  // the few matrices past the last 16-byte granule: straight from global memory
+  if (tail > 0 && blockIdx.x == gridDim.x - 1 && tid < tail) {
+    const i64 b = p.batch - tail + tid;
+    T r0[Op::kLen0], r1[Op::kLen1], r2[Op::kLen2], o[Op::kOut];
+    zero_record(r0);
+    zero_record(r1);
+    zero_record(r2);
+    if (p.present & 1) load_record_scalar(g0 + b * p.in[0].stride, r0);
+    if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1);
+    if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2);
+    apply_op<Op>(p, r0, r1, r2, o);
+    store_record_scalar(gout + b * Op::kOut, o);
   }
 
   int it = 0;
@@ -225,32 +312,28 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
     const uint32_t parity = uint32_t(it / STAGES) & 1u;
     unsigned char* sin = in_base + stage * stage_bytes;
     unsigned char* sout = out_base + (it & 1) * G::kFootOut;
-    const bool ragged = tile >= ntiles;  // at most once, as this CTA's last tile
+    const int cnt = count_of(tile);
 
-    if (!ragged) {
-      mbar_wait(&full[stage], parity);
-    } else {
-      // no bulk copy was issued into this stage: fill it by hand in the same layout
-      const i64 first = tile * TILE;
-      if (staged & 1) coop_load<G, Op::kLen0>(sin, g0 + first * Op::kLen0, rem);
-      if (staged & 2) coop_load<G, Op::kLen1>(sin + f0, g1 + first * Op::kLen1, rem);
-      if (staged & 4) coop_load<G, Op::kLen2>(sin + f0 + f1, g2 + first * Op::kLen2, rem);
-      __syncthreads();
-    }
+    mbar_wait(&full[stage], parity);
+#ifdef NFM_TIMELINE
+    if (it == 0) NFM_STAMP(2);
+#endif
 
     // staged operands come out of shared memory; broadcast (stride 0) operands
-    // are one record for the whole batch, re-read through L1; absent ones are 0
+    // are one record for the whole batch, re-read through L1; absent ones are 0.
+    // Thread slots at or beyond cnt (a tile cut below capacity) compute on
+    // whatever the buffer holds and their results are never stored.
     T r0[MPT][Op::kLen0], r1[MPT][Op::kLen1], r2[MPT][Op::kLen2];
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       const int m = tid + j * THREADS;
-      if (staged & 1) load_record(reinterpret_cast<const T*>(sin + G::template rec_offset<Op::kLen0>(m)), r0[j]);
+      if (staged & 1) load_record(reinterpret_cast<const T*>(sin + G::template rec_offset<Op::kLen0>(m, cnt)), r0[j]);
       else if (p.present & 1) load_record_scalar(g0, r0[j]);
       else zero_record(r0[j]);
-      if (staged & 2) load_record(reinterpret_cast<const T*>(sin + f0 + G::template rec_offset<Op::kLen1>(m)), r1[j]);
+      if (staged & 2) load_record(reinterpret_cast<const T*>(sin + f0 + G::template rec_offset<Op::kLen1>(m, cnt)), r1[j]);
       else if (p.present & 2) load_record_scalar(g1, r1[j]);
       else zero_record(r1[j]);
-      if (staged & 4) load_record(reinterpret_cast<const T*>(sin + f0 + f1 + G::template rec_offset<Op::kLen2>(m)), r2[j]);
+      if (staged & 4) load_record(reinterpret_cast<const T*>(sin + f0 + f1 + G::template rec_offset<Op::kLen2>(m, cnt)), r2[j]);
       else if (p.present & 4) load_record_scalar(g2, r2[j]);
       else zero_record(r2[j]);
     }
@@ -261,32 +344,225 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(const __grid_constant__ K
     __syncthreads();  // every thread has its inputs in registers: stage is free
     if (tid < kIssuers) {
       const i64 nxt = tile + i64(STAGES) * gridDim.x;
-      if (nxt < ntiles) issue(stage, nxt);
+      if (nxt < ntiles_all) issue(stage, nxt);
     }
 
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       T o[Op::kOut];
       apply_op<Op>(p, r0[j], r1[j], r2[j], o);
-      store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(tid + j * THREADS)), o);
-    }
-    if (ragged) {
-      __syncthreads();
-      coop_store<G, Op::kOut>(gout + tile * TILE * Op::kOut, sout, rem);
-      break;
+      // (in the SEG layout a slot beyond cnt would land on the next segment's first record)
+      const int m = tid + j * THREADS;
+      if (m < cnt) store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(m, cnt)), o);
     }
     fence_proxy_async();
     __syncthreads();
     if (tid < kIssuers) {
-      constexpr int nseg = SEG ? kSegs : 1;
-      constexpr int sb = G::kBytesOut / nseg;
       const int seg = SEG ? tid : 0;
-      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * TILE * Op::kOut) + seg * sb,
-               sout + seg * (sb + (SEG ? kSegPad : 0)), sb);
+      const int sbo = (cnt / nseg) * Op::kOut * es;
+      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * tile_m * Op::kOut) + seg * sbo, sout + seg * (sbo + pad), sbo);
       bulk_commit();
     }
   }
-  if (tid < kIssuers) bulk_wait<0>();
+  if (tid < kIssuers) bulk_wait_read<0>();  // writes complete with the grid; only shared memory must outlive them
+  NFM_STAMP(3);
+#ifdef NFM_TIMELINE
+  NFM_STAMP_VAL(4, smid());
+  NFM_STAMP_VAL(5, it);
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// pool_kernel<Op, MAXW, MPT, SEG>(..., nwarps, nbuf)  -- compute-heavy ops (Op::kHeavy:
+// pivoted elimination, Gauss-Jordan) with large records.
+//
+// tile_kernel keeps STAGES input tiles + 2 output tiles per CTA and every
+// thread of the CTA works on the same tile; with 500-800 B records that is
+// ~200 KB of shared memory for 64-128 threads, so an SM holds 2-4 warps whose
+// long dependent chains cannot cover each other (0.23-0.58 of the roofline for
+// dense n >= 8 in round 1).  Here one persistent CTA per SM owns a POOL of nbuf
+// buffers of one warp-tile (32*MPT matrices) each, and its nwarps <= MAXW warps
+// (MAXW only sets the register budget, __launch_bounds__) run independently of
+// each other (no __syncthreads in the loop):
+//   warp-tile l of the CTA  ->  buffer l % nbuf, warp l % nwarps
+//   wait the buffer's mbarrier -> records to registers -> compute -> results
+//   written IN PLACE into the same buffer -> TMA bulk store -> when the store
+//   has read the buffer, the same lane re-arms it with warp-tile l + nbuf.
+// So nwarps buffers are being computed on while nbuf - nwarps are in flight from
+// HBM, and no shared memory is spent on separate output tiles.
+// ---------------------------------------------------------------------------
+template <class Op, int MPT, bool SEG>
+struct PoolGeom {
+  using G = TileGeom<Op, 32, MPT, SEG>;
+  static constexpr int kWarpTile = 32 * MPT;
+  static constexpr int in_bytes(int mask) {
+    return ((mask & 1) ? G::footprint(Op::kLen0) : 0) + ((mask & 2) ? G::footprint(Op::kLen1) : 0) +
+           ((mask & 4) ? G::footprint(Op::kLen2) : 0);
+  }
+  // a buffer holds the staged inputs of one warp-tile, later its outputs
+  static constexpr int buf_bytes(int mask) {
+    const int b = in_bytes(mask) > G::kFootOut ? in_bytes(mask) : G::kFootOut;
+    return (b + 127) / 128 * 128;
+  }
+};
+
+template <class Op, int MAXW, int MPT, bool SEG>
+__global__ void __launch_bounds__(MAXW * 32, 1)
+    pool_kernel(const __grid_constant__ KParams p, const i64 ntiles, const int WARPS, const int NBUF) {
+  using T = typename Op::scalar;
+  using PG = PoolGeom<Op, MPT, SEG>;
+  using G = typename PG::G;
+  constexpr int WT = PG::kWarpTile;
+  constexpr int kIssuers = SEG ? kSegs : 1;
+  constexpr int nseg = SEG ? kSegs : 1;
+  constexpr int pad = SEG ? kSegPad : 0;
+  constexpr bool kHint = Op::kOut >= ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0);
+  NFM_STAMP(0);
+
+  const int rem = int(p.batch - ntiles * WT);
+  const i64 ntiles_all = ntiles + (rem > 0 ? 1 : 0);
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int staged = staged_mask(p);
+  const int f0 = (staged & 1) ? G::footprint(Op::kLen0) : 0;
+  const int f1 = (staged & 2) ? G::footprint(Op::kLen1) : 0;
+  const int buf_bytes = PG::buf_bytes(staged);
+  constexpr int sb0 = G::kBytes0 / nseg, sb1 = G::kBytes1 / nseg, sb2 = G::kBytes2 / nseg, sbo = G::kBytesOut / nseg;
+  const uint32_t tx_bytes = ((staged & 1) ? G::kBytes0 : 0) + ((staged & 2) ? G::kBytes1 : 0) + ((staged & 4) ? G::kBytes2 : 0);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + NBUF * buf_bytes);
+  // gen[b] = generation (l / NBUF) the buffer was last handed over to.  A parity
+  // bit alone cannot tell a consumer that it is TWO phases early (any warp may
+  // consume any buffer here), so a consumer first waits for its generation.
+  int* const gen = reinterpret_cast<int*>(full + NBUF);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* const g0 = static_cast<const T*>(p.in[0].ptr);
+  const T* const g1 = static_cast<const T*>(p.in[1].ptr);
+  const T* const g2 = static_cast<const T*>(p.in[2].ptr);
+  T* const gout = static_cast<T*>(p.out);
+
+  uint64_t policy = 0;
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&full[b], 1);
+      gen[b] = 0;
+    }
+    fence_mbar_init();
+  }
+  if (lane < kIssuers) policy = policy_evict_first();
+#ifndef NFM_NO_PREFETCH
+  // warm L2 with the first nbuf warp-tiles ahead of the dependency wait (see tile_kernel)
+  for (int l = tid; l < NBUF; l += WARPS * 32) {
+    const i64 t = i64(blockIdx.x) + i64(l) * gridDim.x;
+    if (t < ntiles) {
+      const i64 first = t * WT;
+      if (staged & 1) bulk_prefetch_l2(g0 + first * Op::kLen0, G::kBytes0);
+      if (staged & 2) bulk_prefetch_l2(g1 + first * Op::kLen1, G::kBytes1);
+      if (staged & 4) bulk_prefetch_l2(g2 + first * Op::kLen2, G::kBytes2);
+    }
+  }
+#endif
+  __syncthreads();
+  grid_dependency_wait();
+  grid_launch_dependents();
+  NFM_STAMP(1);
+
+  // lanes 0..kIssuers-1 of the calling warp fetch global warp-tile `tile` into buffer `b`
+  auto issue = [&](int b, i64 tile) {
+    unsigned char* dst = smem + b * buf_bytes;
+    const i64 first = tile * WT;
+    if (lane == 0) mbar_arrive_expect_tx(&full[b], tx_bytes);
+    const int seg = SEG ? lane : 0;
+    if (staged & 1)
+      bulk_g2s<kHint>(dst + seg * (sb0 + pad), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb0, sb0,
+                      &full[b], policy);
+    if (staged & 2)
+      bulk_g2s<kHint>(dst + f0 + seg * (sb1 + pad), reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb1,
+                      sb1, &full[b], policy);
+    if (staged & 4)
+      bulk_g2s<kHint>(dst + f0 + f1 + seg * (sb2 + pad),
+                      reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb2, sb2, &full[b], policy);
+  };
+
+  // prologue: fill the pool; local tile l is fetched by the warp that will NOT
+  // necessarily consume it -- any warp may wait on any buffer's barrier
+  if (lane < kIssuers) {
+    for (int l = warp; l < NBUF; l += WARPS) {
+      const i64 t = i64(blockIdx.x) + i64(l) * gridDim.x;
+      if (t < ntiles) issue(l, t);
+    }
+  }
+
+  for (int l = warp;; l += WARPS) {
+    const i64 tile = i64(blockIdx.x) + i64(l) * gridDim.x;
+    if (tile >= ntiles_all) break;
+    const int b = l % NBUF;
+    const uint32_t parity = uint32_t(l / NBUF) & 1u;
+    unsigned char* sbuf = smem + b * buf_bytes;
+    const bool ragged = tile >= ntiles;  // the globally last tile: at most once
+
+    // the buffer's previous user has handed it over to this generation (its
+    // refill has been issued / it is free for the by-hand fill of the ragged tile)
+    while (ld_acquire_shared(&gen[b]) != l / NBUF) {
+    }
+    if (!ragged) {
+      mbar_wait(&full[b], parity);
+#ifdef NFM_TIMELINE
+      if (l == 0) NFM_STAMP(2);
+#endif
+    } else {
+      const i64 first = tile * WT;
+      if (staged & 1) coop_load<G, Op::kLen0>(sbuf, g0 + first * Op::kLen0, rem, WT, lane, 32);
+      if (staged & 2) coop_load<G, Op::kLen1>(sbuf + f0, g1 + first * Op::kLen1, rem, WT, lane, 32);
+      if (staged & 4) coop_load<G, Op::kLen2>(sbuf + f0 + f1, g2 + first * Op::kLen2, rem, WT, lane, 32);
+      __syncwarp();
+    }
+
+    T r0[MPT][Op::kLen0], r1[MPT][Op::kLen1], r2[MPT][Op::kLen2];
+#pragma unroll
+    for (int j = 0; j < MPT; ++j) {
+      const int m = lane + j * 32;
+      if (staged & 1) load_record(reinterpret_cast<const T*>(sbuf + G::template rec_offset<Op::kLen0>(m, WT)), r0[j]);
+      else if (p.present & 1) load_record_scalar(g0, r0[j]);
+      else zero_record(r0[j]);
+      if (staged & 2) load_record(reinterpret_cast<const T*>(sbuf + f0 + G::template rec_offset<Op::kLen1>(m, WT)), r1[j]);
+      else if (p.present & 2) load_record_scalar(g1, r1[j]);
+      else zero_record(r1[j]);
+      if (staged & 4) load_record(reinterpret_cast<const T*>(sbuf + f0 + f1 + G::template rec_offset<Op::kLen2>(m, WT)), r2[j]);
+      else if (p.present & 4) load_record_scalar(g2, r2[j]);
+      else zero_record(r2[j]);
+    }
+    __syncwarp();  // every lane holds its inputs: the buffer now takes the results
+
+#pragma unroll
+    for (int j = 0; j < MPT; ++j) {
+      T o[Op::kOut];
+      apply_op<Op>(p, r0[j], r1[j], r2[j], o);
+      store_record(reinterpret_cast<T*>(sbuf + G::template rec_offset<Op::kOut>(lane + j * 32, WT)), o);
+    }
+    if (ragged) {
+      __syncwarp();
+      coop_store<G, Op::kOut>(gout + tile * WT * Op::kOut, sbuf, rem, WT, lane, 32);
+      break;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    const i64 nxt = tile + i64(NBUF) * gridDim.x;  // next user of this buffer
+    if (lane < kIssuers) {
+      const int seg = SEG ? lane : 0;
+      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * WT * Op::kOut) + seg * sbo, sbuf + seg * (sbo + pad), sbo);
+      bulk_commit();
+      if (nxt < ntiles_all) bulk_wait_read<0>();  // the store has read the buffer: it can be refilled
+    }
+    if (nxt < ntiles_all) {
+      if constexpr (SEG) __syncwarp();  // every segment's store has been read before any lane refills
+      if (nxt < ntiles && lane < kIssuers) issue(b, nxt);
+      if constexpr (SEG) __syncwarp();  // lane 0's arrive.expect_tx and every segment's copy are issued
+      if (lane == 0) st_release_shared(&gen[b], l / NBUF + 1);
+    }
+  }
+  if (lane < kIssuers) bulk_wait<0>();
+  NFM_STAMP(3);
 }
 
 template <class Op>
@@ -298,7 +574,11 @@ __global__ void __launch_bounds__(128) strided_kernel(const __grid_constant__ KP
   T* const gout = static_cast<T*>(p.out);
   grid_dependency_wait();
   grid_launch_dependents();
-  for (i64 b = i64(blockIdx.x) * blockDim.x + threadIdx.x; b < p.batch; b += i64(gridDim.x) * blockDim.x) {
+  // block-uniform trip count (ops may vote across the warp): lanes past the end
+  // redo the last matrix and do not store
+  for (i64 b0 = i64(blockIdx.x) * blockDim.x; b0 < p.batch; b0 += i64(gridDim.x) * blockDim.x) {
+    const bool valid = b0 + threadIdx.x < p.batch;
+    const i64 b = valid ? b0 + threadIdx.x : p.batch - 1;
     T r0[Op::kLen0], r1[Op::kLen1], r2[Op::kLen2], o[Op::kOut];
     zero_record(r0);
     zero_record(r1);
@@ -307,7 +587,7 @@ __global__ void __launch_bounds__(128) strided_kernel(const __grid_constant__ KP
     if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1, elem_stride(p.in[1].estride));
     if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2, elem_stride(p.in[2].estride));
     apply_op<Op>(p, r0, r1, r2, o);
-    store_record_scalar(gout + b * p.out_stride, o, elem_stride(p.out_estride));
+    if (valid) store_record_scalar(gout + b * p.out_stride, o, elem_stride(p.out_estride));
   }
 }
 
@@ -424,6 +704,44 @@ struct TuneSmall {
   static constexpr int kTilesPerCtaBelow = 20;  // use it when the big geometry would give fewer tiles per SM than this
 };
 
+// Pool geometry for compute-heavy ops with large records (pool_kernel).
+// Measured on B200 (profiles/r2_pool_sweep.txt): the pool wins from ~256 B of
+// input per matrix (fp64 8x8 inverse 0.43 -> 0.86 of the measured peak, fp32
+// 10x10 0.66 -> 0.93) and loses below (4x4 fp64 inverse 0.90 vs 0.95).
+//   kMaxW : register budget (launch bounds) from the scalars a thread keeps live
+//           (Op::kLive when the op expands its record, else its input record)
+//   warps / buffers at run time: as many warps as that budget allows while
+//           ~1/4 of the pool (at least 2 buffers, at most ~80 KB) stays in flight.
+template <class Op, class = void>
+struct live_scalars { static constexpr int value = ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0); };
+template <class Op>
+struct live_scalars<Op, std::void_t<decltype(Op::kLive)>> { static constexpr int value = Op::kLive; };
+
+template <class Op>
+struct PoolTune {
+  using B = TuneBase<Op>;
+  static constexpr int kLiveWords = live_scalars<Op>::value * int(sizeof(typename Op::scalar)) / 4;
+#ifdef NFM_TUNE_POOL
+  static constexpr bool kEnabled = NFM_TUNE_POOL && Op::kHeavy;
+#else
+  static constexpr bool kEnabled = Op::kHeavy && B::kInBytes >= 256;
+#endif
+  static constexpr int kMaxW = kLiveWords <= 64 ? 16 : kLiveWords <= 112 ? 12 : 8;
+  static constexpr int kMpt = 1;
+  static void geometry(int buf_bytes, int max_smem, int& warps, int& nbuf) {
+    int nbuf_max = (max_smem - 512) / (buf_bytes + 12);
+    if (nbuf_max > 24) nbuf_max = 24;
+    int flight = (80 * 1024 + buf_bytes - 1) / buf_bytes;
+    const int cap = nbuf_max / 4 > 2 ? nbuf_max / 4 : 2;
+    if (flight > cap) flight = cap;
+    if (flight < 2) flight = 2;
+    warps = nbuf_max - flight < kMaxW ? nbuf_max - flight : kMaxW;
+    if (warps < 1) warps = 1;
+    nbuf = nbuf_max < 3 * warps ? nbuf_max : 3 * warps;
+    if (nbuf <= warps) nbuf = warps + 1;
+  }
+};
+
 bool pdl_enabled();  // nfm_entry.cu: false when the environment has NFM_DISABLE_PDL=1
 
 // Launch with programmatic stream serialization: the kernel may become resident
@@ -450,8 +768,23 @@ struct LaunchCache {
   std::atomic<int> attr_set[16];
 };
 
+// Equal tiles: a launch of `batch` matrices on `grid_max` persistent CTAs takes
+// waves = ceil(batch / (grid_max * capacity)) tiles per CTA; cutting the tile to
+// ceil(batch / (grid_max * waves)) matrices (rounded up to kTileGran) gives every
+// CTA the same number of (slightly smaller) tiles instead of leaving a last,
+// partly filled wave -- 9.2 waves of 512-matrix tiles became 10 of 480 for a
+// 2M-matrix slab.  Large launches keep the full capacity (the rounding absorbs it).
+inline int balanced_tile(i64 batch, i64 grid_max, int capacity) {
+  const i64 waves = (batch + grid_max * capacity - 1) / (grid_max * capacity);
+  i64 t = (batch + grid_max * waves - 1) / (grid_max * waves);
+  t = (t + kTileGran - 1) / kTileGran * kTileGran;
+  return int(t < capacity ? t : capacity);
+}
+
+bool balance_enabled();  // nfm_entry.cu: false when the environment has NFM_DISABLE_BALANCE=1
+
 template <class Op, int THREADS, int MPT, int STAGES, bool SEG>
-int launch_tile(const KParams& p, i64 ntiles, cudaStream_t stream) {
+int launch_tile(const KParams& p, cudaStream_t stream) {
   using G = TileGeom<Op, THREADS, MPT, SEG>;
   static LaunchCache cache;  // zero-initialised
   auto kern = tile_kernel<Op, THREADS, MPT, STAGES, SEG>;
@@ -479,10 +812,46 @@ int launch_tile(const KParams& p, i64 ntiles, cudaStream_t stream) {
     if (per_sm < 1) return -1;
     cache.per_sm[d][staged].store(per_sm, std::memory_order_release);
   }
-  const i64 ntiles_all = ntiles + (p.batch > ntiles * G::kTile ? 1 : 0);
-  i64 grid = i64(dev.sm_count) * per_sm;
+  const i64 grid_max = i64(dev.sm_count) * per_sm;
+  const int tile_m = balance_enabled() ? balanced_tile(p.batch, grid_max, G::kTile) : G::kTile;
+  const i64 ntiles = p.batch / tile_m;
+  const int part_m = int(p.batch - ntiles * tile_m) / G::kGran * G::kGran;
+  i64 ntiles_all = ntiles + (part_m > 0 ? 1 : 0);
+  if (ntiles_all == 0) ntiles_all = 1;  // only a direct tail
+  const i64 grid = grid_max < ntiles_all ? grid_max : ntiles_all;
+  cudaError_t e = launch_pdl(kern, unsigned(grid), THREADS, size_t(smem), stream, p, ntiles, tile_m, part_m);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(e);
+}
+
+template <class Op, int MAXW, int MPT, bool SEG>
+int launch_pool(const KParams& p, int nwarps, int nbuf, cudaStream_t stream) {
+  using PG = PoolGeom<Op, MPT, SEG>;
+  static LaunchCache cache;  // attr_set only
+  auto kern = pool_kernel<Op, MAXW, MPT, SEG>;
+  const int staged = staged_mask(p);
+  const DeviceInfo& dev = device_info();
+  // optional / broadcast operands change the buffer size: keep the pool inside the
+  // shared-memory limit by dropping buffers (never below nwarps + 1)
+  auto smem_for = [&](int nb) { return nb * PG::buf_bytes(staged) + nb * 12 + 16; };
+  while (nbuf > nwarps + 1 && smem_for(nbuf) > dev.max_smem_optin) --nbuf;
+  while (nwarps > 1 && smem_for(nbuf) > dev.max_smem_optin) {
+    --nwarps;
+    nbuf = nwarps + 1;
+  }
+  const int smem = smem_for(nbuf);
+  if (smem > dev.max_smem_optin || nwarps < 1 || nwarps > MAXW || nbuf <= nwarps) return -1;
+  const int d = current_device() & 15;
+  if (!cache.attr_set[d].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
+    if (e != cudaSuccess) return int(e);
+    cache.attr_set[d].store(1, std::memory_order_release);
+  }
+  const i64 ntiles = p.batch / PG::kWarpTile;
+  const i64 ntiles_all = ntiles + (p.batch > ntiles * PG::kWarpTile ? 1 : 0);
+  i64 grid = dev.sm_count;  // one persistent CTA per SM
   if (grid > ntiles_all) grid = ntiles_all;
-  cudaError_t e = launch_pdl(kern, unsigned(grid), THREADS, size_t(smem), stream, p, ntiles);
+  cudaError_t e = launch_pdl(kern, unsigned(grid), unsigned(nwarps * 32), size_t(smem), stream, p, ntiles, nwarps, nbuf);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return int(e);
 }
@@ -521,14 +890,21 @@ int run_op(KParams p, cudaStream_t stream) {
   if (fast) {
     // full tiles by TMA, the ragged remainder inside the same launch
     int rc;
+    if constexpr (PoolTune<Op>::kEnabled) {
+      using Pt = PoolTune<Op>;
+      int warps, nbuf;
+      Pt::geometry(PoolGeom<Op, Pt::kMpt, Tn::kSeg>::buf_bytes(staged_mask(p)), device_info().max_smem_optin, warps, nbuf);
+      rc = launch_pool<Op, Pt::kMaxW, Pt::kMpt, Tn::kSeg>(p, warps, nbuf, stream);
+    } else {
     bool small = false;
     if constexpr (TuneSmall<Op>::kEnabled) small = p.batch / TILE < i64(TuneSmall<Op>::kTilesPerCtaBelow) * device_info().sm_count;
     if constexpr (TuneSmall<Op>::kEnabled) {
       using Ts = TuneSmall<Op>;
-      rc = small ? launch_tile<Op, Ts::kThreads, Ts::kMpt, Ts::kStages, Tn::kSeg>(p, p.batch / (Ts::kThreads * Ts::kMpt), stream)
-                 : launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, p.batch / TILE, stream);
+      rc = small ? launch_tile<Op, Ts::kThreads, Ts::kMpt, Ts::kStages, Tn::kSeg>(p, stream)
+                 : launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, stream);
     } else {
-      rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, p.batch / TILE, stream);
+      rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, stream);
+    }
     }
     if (rc == 0) {
       t_last_path_tma = 1;

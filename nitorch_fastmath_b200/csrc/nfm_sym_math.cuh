@@ -323,23 +323,25 @@ struct GaussPP {
           p = i;
         }
       });
-      static_for<k + 1, N>([&](auto I) {
-        constexpr int i = I;
-        const bool sw = (p == i);
-        static_for<k, N>([&](auto J) {
-          constexpr int j = J;
-          const T lo = a[k][j], hi = a[i][j];
-          a[k][j] = sw ? hi : lo;
-          a[i][j] = sw ? lo : hi;
+      if (warp_any(p != k)) {  // skipped when no matrix of the warp exchanges rows in this step
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const bool sw = (p == i);
+          static_for<k, N>([&](auto J) {
+            constexpr int j = J;
+            const T lo = a[k][j], hi = a[i][j];
+            a[k][j] = sw ? hi : lo;
+            a[i][j] = sw ? lo : hi;
+          });
+          static_for<0, R>([&](auto C) {
+            constexpr int c = C;
+            const T lo = b[k][c], hi = b[i][c];
+            b[k][c] = sw ? hi : lo;
+            b[i][c] = sw ? lo : hi;
+          });
         });
-        static_for<0, R>([&](auto C) {
-          constexpr int c = C;
-          const T lo = b[k][c], hi = b[i][c];
-          b[k][c] = sw ? hi : lo;
-          b[i][c] = sw ? lo : hi;
-        });
-      });
-      if (p != k) det_sign = -det_sign;
+        if (p != k) det_sign = -det_sign;
+      }
       const T rp = T(1) / a[k][k];
       static_for<k + 1, N>([&](auto I) {
         constexpr int i = I;

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <array>
 #include <vector>
 
 #include "nfm_dense_ops.cuh"
@@ -24,6 +26,8 @@ const DeviceInfo& device_info() {
 }
 int current_device() { return 0; }
 bool pdl_enabled() { return true; }
+bool g_balance = true;
+bool balance_enabled() { return g_balance; }
 }  // namespace nfm
 
 using namespace nfm;
@@ -58,13 +62,12 @@ void run_config(const char* name, const Buffers& b, int alg_bytes) {
   p.out = b.out;
   p.out_stride = Op::kOut;
   constexpr int TILE = THREADS * MPT;
-  const i64 ntiles = b.batch / TILE;
   p.batch = b.batch;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   int rc = 0;
-  for (int i = 0; i < 3 && rc == 0; ++i) rc = launch_tile<Op, THREADS, MPT, STAGES, SEG>(p, ntiles, 0);
+  for (int i = 0; i < 3 && rc == 0; ++i) rc = launch_tile<Op, THREADS, MPT, STAGES, SEG>(p, 0);
   if (rc != 0) {
     printf("%-22s T=%4d thr=%3d st=%d seg=%d : launch failed rc=%d\n", name, TILE, THREADS, STAGES, int(SEG), rc);
     cudaGetLastError();
@@ -73,7 +76,7 @@ void run_config(const char* name, const Buffers& b, int alg_bytes) {
   cudaDeviceSynchronize();
   const int reps = 20;
   cudaEventRecord(e0);
-  for (int i = 0; i < reps; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(p, ntiles, 0);
+  for (int i = 0; i < reps; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(p, 0);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms = 0;
@@ -90,19 +93,20 @@ void run_config(const char* name, const Buffers& b, int alg_bytes) {
 template <class Op, int THREADS, int MPT, int STAGES, bool SEG>
 void run_sliced(const char* name, const Buffers& b, int alg_bytes, i64 sub) {
   using T = typename Op::scalar;
-  const int slices = int(b.batch / sub);
+  const i64 pitch = (sub + 1023) / 1024 * 1024;  // slices start 16-byte aligned for any sub
+  const int slices = int(b.batch / pitch);
   std::vector<KParams> ps(slices);
   for (int s = 0; s < slices; ++s) {
     KParams p{};
-    p.in[0].ptr = static_cast<const T*>(b.in0) + i64(s) * sub * Op::kLen0;
+    p.in[0].ptr = static_cast<const T*>(b.in0) + i64(s) * pitch * Op::kLen0;
     p.in[0].stride = Op::kLen0;
     p.present = 1;
     if (Op::kUse & 2) {
-      p.in[1].ptr = static_cast<const T*>(b.in1) + i64(s) * sub * Op::kLen1;
+      p.in[1].ptr = static_cast<const T*>(b.in1) + i64(s) * pitch * Op::kLen1;
       p.in[1].stride = Op::kLen1;
       p.present |= 2;
     }
-    p.out = static_cast<T*>(b.out) + i64(s) * sub * Op::kOut;
+    p.out = static_cast<T*>(b.out) + i64(s) * pitch * Op::kOut;
     p.out_stride = Op::kOut;
     p.batch = sub;
     ps[s] = p;
@@ -111,11 +115,11 @@ void run_sliced(const char* name, const Buffers& b, int alg_bytes, i64 sub) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  for (int i = 0; i < slices; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i], sub / TILE, 0);
+  for (int i = 0; i < slices; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i], 0);
   cudaDeviceSynchronize();
   const int reps = 10 * slices;
   cudaEventRecord(e0);
-  for (int i = 0; i < reps; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i % slices], sub / TILE, 0);
+  for (int i = 0; i < reps; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i % slices], 0);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms = 0;
@@ -124,6 +128,94 @@ void run_sliced(const char* name, const Buffers& b, int alg_bytes, i64 sub) {
   printf("%-18s batch %8lld T=%4d thr=%3d st=%d : %7.2f us  %7.1f GB/s\n", name, sub, TILE, THREADS, STAGES, us,
          double(sub) * alg_bytes / (us * 1e-6) / 1e9);
   fflush(stdout);
+}
+
+template <typename T>
+__global__ void diff_kernel(const T* a, const T* b, i64 n, unsigned long long* bad) {
+  for (i64 i = i64(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += i64(gridDim.x) * blockDim.x)
+    if (!(a[i] == b[i]) && !(a[i] != a[i] && b[i] != b[i])) atomicAdd(bad, 1ull);
+}
+
+// pool_kernel configuration; checks its output bit for bit against tile_kernel's
+template <class Op, int MAXW, int MPT, bool SEG>
+void run_pool(const char* name, const Buffers& b, int alg_bytes, int W, int NBUF) {
+  using T = typename Op::scalar;
+  KParams p{};
+  p.in[0].ptr = b.in0;
+  p.in[0].stride = Op::kLen0;
+  p.present = 1;
+  if (Op::kUse & 2) {
+    p.in[1].ptr = b.in1;
+    p.in[1].stride = Op::kLen1;
+    p.present |= 2;
+  }
+  p.out_stride = Op::kOut;
+  p.batch = b.batch;
+  const int buf = PoolGeom<Op, MPT, SEG>::buf_bytes(p.present);
+  if (W == 0) PoolTune<Op>::geometry(buf, device_info().max_smem_optin, W, NBUF);  // the rule
+  if (W > MAXW || NBUF <= W || NBUF * (buf + 12) + 16 > device_info().max_smem_optin) return;
+  // reference result from the tile kernel into a scratch buffer
+  static T* ref = nullptr;
+  static const void* ref_for = nullptr;
+  int rc = 0;
+  if (ref_for != b.in0) {
+    if (ref) cudaFree(ref);
+    cudaMalloc(&ref, size_t(p.batch) * Op::kOut * sizeof(T));
+    p.out = ref;
+    using Tn = Tune<Op>;
+    rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, 0);
+    ref_for = b.in0;
+  }
+  p.out = b.out;
+  cudaMemset(b.out, 0xff, size_t(p.batch) * Op::kOut * sizeof(T));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 3 && rc == 0; ++i) rc = launch_pool<Op, MAXW, MPT, SEG>(p, W, NBUF, 0);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (rc != 0 || err != cudaSuccess) {
+    printf("%-20s pool maxw=%2d W=%2d mpt=%d nbuf=%2d seg=%d : failed rc=%d %s (%s)\n", name, MAXW, W, MPT, NBUF, int(SEG), rc,
+           cudaGetErrorString(err), cudaGetErrorName(err));
+    cudaGetLastError();
+    return;
+  }
+  unsigned long long* bad;
+  cudaMalloc(&bad, 8);
+  cudaMemset(bad, 0, 8);
+  diff_kernel<T><<<1184, 256>>>(ref, static_cast<const T*>(b.out), p.batch * Op::kOut, bad);
+  unsigned long long hbad = 0;
+  cudaMemcpy(&hbad, bad, 8, cudaMemcpyDeviceToHost);
+  const int reps = 10;
+  cudaEventRecord(e0);
+  for (int i = 0; i < reps; ++i) launch_pool<Op, MAXW, MPT, SEG>(p, W, NBUF, 0);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double us = ms * 1e3 / reps;
+  printf("%-20s pool maxw=%2d W=%2d mpt=%d nbuf=%2d seg=%d smem=%3dK : %8.1f us  %7.1f GB/s  mismatches %llu\n", name, MAXW, W, MPT,
+         NBUF, int(SEG), (NBUF * (buf + 12) + 16) >> 10, us, double(p.batch) * alg_bytes / (us * 1e-6) / 1e9, hbad);
+  fflush(stdout);
+  cudaFree(bad);
+}
+
+// rule + a grid of (warps, buffers) for two register budgets
+template <class Op>
+void pool_sweep(const char* name, const Buffers& buf, int alg_bytes) {
+  constexpr bool SEG = Tune<Op>::kSeg;
+  constexpr int RW = PoolTune<Op>::kMaxW;
+  run_pool<Op, RW, 1, SEG>(name, buf, alg_bytes, 0, 0);
+  printf("   ^ rule\n");
+  const int nmax = (device_info().max_smem_optin - 512) / (PoolGeom<Op, 1, SEG>::buf_bytes(Op::kUse & 3) + 12);
+  for (int w : {4, 5, 6, 7, 8})
+    for (int nb : {w + 1, w + 2, w + 3, w + 5, nmax})
+      if (nb <= nmax && nb <= 32) run_pool<Op, 8, 1, SEG>(name, buf, alg_bytes, w, nb);
+  for (int w : {10, 12})
+    for (int nb : {w + 2, w + 4, w + 6, nmax})
+      if (nb <= nmax && nb <= 32) run_pool<Op, 12, 1, SEG>(name, buf, alg_bytes, w, nb);
+  for (int w : {14, 16})
+    for (int nb : {w + 4, w + 8, nmax})
+      if (nb <= nmax && nb <= 32) run_pool<Op, 16, 1, SEG>(name, buf, alg_bytes, w, nb);
 }
 
 template <typename T>
@@ -177,6 +269,212 @@ int main(int argc, char** argv) {
     }
     release(buf);
   }
+  if (want("balance")) {
+    // equal-tile scheduling on / off for mid-size launches (a multi-GPU slab, config 1)
+    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
+    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
+    for (i64 sub : {i64(1000000), i64(1) << 20, i64(2000003), i64(1) << 21, i64(1) << 22, i64(1) << 23}) {
+      for (int bal = 0; bal < 2; ++bal) {
+        g_balance = bal;
+        printf("balance=%d ", bal);
+        run_sliced<Op, 512, 2, 3, false>("solve3", buf, 48, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op, 256, 2, 3, false>("solve3", buf, 48, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op, 256, 1, 3, false>("solve3", buf, 48, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op, 128, 2, 4, false>("solve3", buf, 48, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op, 1024, 1, 3, false>("solve3", buf, 48, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op, 512, 1, 4, false>("solve3", buf, 48, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op, 256, 2, 4, false>("solve3", buf, 48, sub);
+      }
+    }
+    g_balance = true;
+    release(buf);
+    using Op6 = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    Buffers b6 = make<float>(192ll * 192 * 192, 21, 6, 6, 6);
+    for (i64 sub : {i64(884736), i64(1769472)}) {   // 192^3 / 8, / 4
+      for (int bal = 0; bal < 2; ++bal) {
+        g_balance = bal;
+        printf("balance=%d ", bal);
+        run_sliced<Op6, 512, 1, 2, false>("solve6", b6, 132, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op6, 256, 1, 2, false>("solve6", b6, 132, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op6, 256, 1, 3, false>("solve6", b6, 132, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op6, 128, 1, 3, false>("solve6", b6, 132, sub);
+      }
+    }
+    g_balance = true;
+    release(b6);
+    using Oi6 = SymInvertOp<float, 6, NFM_ALGO_AUTO, false>;
+    Buffers bi6 = make<float>(192ll * 192 * 192, 21, 6, 0, 21);
+    for (i64 sub : {i64(884736), i64(1769472)}) {
+      for (int bal = 0; bal < 2; ++bal) {
+        g_balance = bal;
+        printf("balance=%d ", bal);
+        run_sliced<Oi6, 384, 1, 2, false>("invert6", bi6, 168, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Oi6, 256, 1, 2, false>("invert6", bi6, 168, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Oi6, 128, 1, 3, false>("invert6", bi6, 168, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Oi6, 128, 1, 2, false>("invert6", bi6, 168, sub);
+      }
+    }
+    g_balance = true;
+    release(bi6);
+    using Op10 = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    Buffers b10 = make<float>(160ll * 160 * 160, 55, 10, 10, 10);
+    for (i64 sub : {i64(512000), i64(1024000)}) {   // 160^3 / 8, / 4
+      for (int bal = 0; bal < 2; ++bal) {
+        g_balance = bal;
+        printf("balance=%d ", bal);
+        run_sliced<Op10, 256, 1, 2, false>("solve10", b10, 300, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op10, 128, 1, 2, false>("solve10", b10, 300, sub);
+        printf("balance=%d ", bal);
+        run_sliced<Op10, 128, 1, 3, false>("solve10", b10, 300, sub);
+      }
+    }
+    g_balance = true;
+    release(b10);
+  }
+#define TILE_RULE(OP, NAME, BYTES) \
+  run_config<OP, Tune<OP>::kThreads, Tune<OP>::kMpt, Tune<OP>::kStages, Tune<OP>::kSeg>(NAME " tile-rule", buf, BYTES)
+#define POOLBLOCK(TAG, OP, T, NAME, BATCH, L0, ND, L1, LO, BYTES) \
+  if (want(TAG)) {                                                 \
+    Buffers buf = make<T>(BATCH, L0, ND, L1, LO);                  \
+    TILE_RULE(OP, NAME, BYTES);                                    \
+    pool_sweep<OP>(NAME, buf, BYTES);                              \
+    release(buf);                                                  \
+  }
+  using InvD8 = BatchInvOp<double, 8, NFM_ALGO_AUTO>;
+  using InvD10 = BatchInvOp<double, 10, NFM_ALGO_AUTO>;
+  using InvD6 = BatchInvOp<double, 6, NFM_ALGO_AUTO>;
+  using InvF10 = BatchInvOp<float, 10, NFM_ALGO_AUTO>;
+  using InvF8 = BatchInvOp<float, 8, NFM_ALGO_AUTO>;
+  using DetD10 = BatchDetOp<double, 10>;
+  using SolD10 = BatchSolveOp<double, 10, NFM_ALGO_LU>;
+  using SolD8 = BatchSolveOp<double, 8, NFM_ALGO_LU>;
+  using SolF10 = BatchSolveOp<float, 10, NFM_ALGO_LU>;
+  using SymLuF10 = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LU>;
+  using SymLuD10 = SymSolveOp<double, 10, NFM_LAYOUT_SYM, NFM_ALGO_LU>;
+  POOLBLOCK("pool_inv8d", InvD8, double, "inv8 f64", 4ll << 20, 64, -8, 0, 64, 1024)
+  POOLBLOCK("pool_inv10d", InvD10, double, "inv10 f64", 4ll << 20, 100, -10, 0, 100, 1600)
+  POOLBLOCK("pool_inv6d", InvD6, double, "inv6 f64", 8ll << 20, 36, -6, 0, 36, 576)
+  POOLBLOCK("pool_inv10f", InvF10, float, "inv10 f32", 8ll << 20, 100, -10, 0, 100, 800)
+  POOLBLOCK("pool_inv8f", InvF8, float, "inv8 f32", 8ll << 20, 64, -8, 0, 64, 512)
+  POOLBLOCK("pool_det10d", DetD10, double, "det10 f64", 4ll << 20, 100, -10, 0, 1, 808)
+  POOLBLOCK("pool_solve10d", SolD10, double, "solve10 f64", 4ll << 20, 100, -10, 10, 10, 960)
+  POOLBLOCK("pool_solve8d", SolD8, double, "solve8 f64", 4ll << 20, 64, -8, 8, 8, 640)
+  POOLBLOCK("pool_solve10f", SolF10, float, "solve10 f32", 8ll << 20, 100, -10, 10, 10, 480)
+  POOLBLOCK("pool_symlu10f", SymLuF10, float, "symlu10 f32", 160ll * 160 * 160, 55, 10, 10, 10, 300)
+  POOLBLOCK("pool_symlu10d", SymLuD10, double, "symlu10 f64", 160ll * 160 * 160, 55, 10, 10, 10, 600)
+#ifdef NFM_TIMELINE
+  if (want("timeline")) {
+    // ramp / steady / tail of back-to-back launches from per-CTA %globaltimer stamps:
+    // 0 = CTA start, 1 = after griddepcontrol.wait, 2 = first tile landed, 3 = CTA end
+    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
+    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
+    const int nl = 10;
+    unsigned long long* d_tl;
+    const size_t slots = size_t(nl) * 1024 * 8;
+    cudaMalloc(&d_tl, slots * 8);
+    cudaMemcpyToSymbol(g_timeline, &d_tl, sizeof(d_tl));
+    auto run = [&](const char* label, i64 sub, auto launcher, bool dump = false) {
+      const i64 pitch = (sub + 1023) / 1024 * 1024;
+      const int slices = int(buf.batch / pitch);
+      std::vector<KParams> ps(nl);
+      for (int i = 0; i < nl; ++i) {
+        const int s = i % slices;
+        KParams p{};
+        p.in[0].ptr = static_cast<const float*>(buf.in0) + i64(s) * pitch * 6;
+        p.in[0].stride = 6;
+        p.in[1].ptr = static_cast<const float*>(buf.in1) + i64(s) * pitch * 3;
+        p.in[1].stride = 3;
+        p.present = 3;
+        p.out = static_cast<float*>(buf.out) + i64(s) * pitch * 3;
+        p.out_stride = 3;
+        p.batch = sub;
+        p.scal1 = i;
+        ps[i] = p;
+      }
+      for (int i = 0; i < nl; ++i) launcher(ps[i]);  // warm-up
+      cudaDeviceSynchronize();
+      cudaMemset(d_tl, 0, slots * 8);
+      cudaDeviceSynchronize();
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0);
+      for (int i = 0; i < nl; ++i) launcher(ps[i]);
+      cudaEventRecord(e1);
+      cudaDeviceSynchronize();
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      std::vector<unsigned long long> h(slots);
+      cudaMemcpy(h.data(), d_tl, slots * 8, cudaMemcpyDeviceToHost);
+      printf("== timeline %s: %lld matrices per launch, %d back-to-back launches, %.2f us per launch by events\n", label, sub, nl,
+             ms * 1e3 / nl);
+      printf("   launch ctas | start: first..last | dep-wait passed: first..last | first tile: first..median..last | end: first..last | prev end -> first dep-wait | dep-wait -> last end\n");
+      unsigned long long prev_end = 0;
+      for (int i = 0; i < nl; ++i) {
+        std::vector<unsigned long long> s0, s1, s2, s3;
+        for (int c = 0; c < 1024; ++c) {
+          const unsigned long long* r = &h[(size_t(i) * 1024 + c) * 8];
+          if (r[3] == 0) continue;
+          s0.push_back(r[0]);
+          s1.push_back(r[1]);
+          if (r[2]) s2.push_back(r[2]);
+          s3.push_back(r[3]);
+        }
+        if (s0.empty()) continue;
+        auto srt = [](std::vector<unsigned long long>& v) { std::sort(v.begin(), v.end()); };
+        srt(s0); srt(s1); srt(s2); srt(s3);
+        const unsigned long long t0 = s0.front();
+        auto rel = [&](unsigned long long t) { return (long long)(t - t0); };
+        printf("   %2d %4zu | %6lld..%6lld | %6lld..%6lld | %6lld..%6lld..%6lld | %6lld..%6lld | %6lld | %6lld\n", i, s0.size(),
+               rel(s0.front()), rel(s0.back()), rel(s1.front()), rel(s1.back()), s2.empty() ? 0 : rel(s2.front()),
+               s2.empty() ? 0 : rel(s2[s2.size() / 2]), s2.empty() ? 0 : rel(s2.back()), rel(s3.front()), rel(s3.back()),
+               prev_end ? (long long)(s1.front() - prev_end) : 0, (long long)(s3.back() - s1.front()));
+        prev_end = s3.back();
+      }
+      if (dump) {
+        const int i = 5;
+        unsigned long long t1 = ~0ull;
+        for (int c = 0; c < 1024; ++c) {
+          const unsigned long long* r = &h[(size_t(i) * 1024 + c) * 8];
+          if (r[3] && r[1] < t1) t1 = r[1];
+        }
+        std::vector<std::array<long long, 5>> rows;
+        for (int c = 0; c < 1024; ++c) {
+          const unsigned long long* r = &h[(size_t(i) * 1024 + c) * 8];
+          if (r[3] == 0) continue;
+          rows.push_back({(long long)r[4], (long long)c, (long long)r[5], (long long)(r[2] ? r[2] - t1 : 0), (long long)(r[3] - t1)});
+        }
+        std::sort(rows.begin(), rows.end());
+        printf("   per-CTA (launch 5): sm cta tiles first_tile_ns end_ns\n");
+        for (auto& r : rows) printf("   sm %3lld cta %3lld tiles %2lld first %5lld end %5lld\n", r[0], r[1], r[2], r[3], r[4]);
+      }
+      fflush(stdout);
+    };
+    for (i64 sub : {i64(1) << 21, i64(1000000)}) {
+      g_balance = false;
+      run("solve3 512x2 st3 (1 CTA/SM), fixed 1024 tiles", sub, [](const KParams& p) { launch_tile<Op, 512, 2, 3, false>(p, 0); });
+      run("solve3 256x2 st3 (3 CTA/SM), fixed 512 tiles", sub, [](const KParams& p) { launch_tile<Op, 256, 2, 3, false>(p, 0); },
+          sub == (i64(1) << 21));
+      run("solve3 128x2 st4, fixed 256 tiles", sub, [](const KParams& p) { launch_tile<Op, 128, 2, 4, false>(p, 0); });
+      g_balance = true;
+      run("solve3 256x2 st3 (3 CTA/SM), equal tiles", sub, [](const KParams& p) { launch_tile<Op, 256, 2, 3, false>(p, 0); });
+    }
+    release(buf);
+  }
+#endif
   if (want("solve6")) {
     using Op = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
     using Ldl = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_LDL>;
