@@ -174,6 +174,8 @@ __device__ __forceinline__ void static_for_down(F&& f) {
 // step in which no matrix of the warp pivots (always, on diagonally dominant or
 // SPD input); correctness does not depend on which lanes take part.
 __device__ __forceinline__ bool warp_any(bool pred) { return __any_sync(__activemask(), pred) != 0; }
+// below this order the exchanges are cheaper than the votes and branches that would skip them
+constexpr int kVoteFromOrder = 6;
 
 // programmatic dependent launch (PDL)
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -94,7 +94,7 @@ struct GaussJordan {
         }
       });
       piv[k] = p;
-      if (warp_any(p != k)) {  // skipped when no matrix of the warp exchanges rows in this step
+      if (N < kVoteFromOrder || warp_any(p != k)) {  // skipped when no matrix of the warp exchanges rows in this step
         static_for<k + 1, N>([&](auto I) {
           constexpr int i = I;
           const bool sw = (p == i);
@@ -124,7 +124,7 @@ struct GaussJordan {
     // (P A)^-1 = A^-1 P^T  ->  undo with column swaps in reverse order
     static_for_down<0, N>([&](auto K) {
       constexpr int k = K;
-      if (warp_any(piv[k] != k)) {
+      if (N < kVoteFromOrder || warp_any(piv[k] != k)) {
         static_for<k + 1, N>([&](auto C) {
           constexpr int c = C;
           const bool sw = (piv[k] == c);

@@ -46,9 +46,11 @@ bool pdl_enabled() {
 }
 
 bool balance_enabled() {
+  // equal-tile scheduling (balanced_tile): measured neutral once the partial tile moves by TMA
+  // (profiles/r2_geometry_sweep.txt), so it is off unless NFM_BALANCE=1
   static const bool on = [] {
-    const char* v = std::getenv("NFM_DISABLE_BALANCE");
-    return !(v != nullptr && v[0] == '1');
+    const char* v = std::getenv("NFM_BALANCE");
+    return v != nullptr && v[0] == '1';
   }();
   return on;
 }

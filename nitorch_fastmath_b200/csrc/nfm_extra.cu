@@ -14,7 +14,6 @@ struct SymDetOp {
   using scalar = T;
   static constexpr int kLen0 = packed_len(N), kLen1 = 1, kLen2 = 1, kUse = 1, kOut = 1;
   static constexpr bool kHeavy = N > 4;
-  static constexpr int kLive = N > 4 ? N * N : kLen0;
   __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&)[1], const T (&)[1], int, int, T (&out)[1]) {
     if constexpr (N <= 4) {
       out[0] = sym_det_closed<T, N>(m);

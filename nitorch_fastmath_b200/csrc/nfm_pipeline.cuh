@@ -89,13 +89,15 @@ struct TileGeom {
   static_assert(kBytes0 % 16 == 0 && kBytes1 % 16 == 0 && kBytes2 % 16 == 0 && kBytesOut % 16 == 0,
                 "tile byte counts must be multiples of 16 for TMA bulk copies");
 
-  // byte offset of record m (0 <= m < tile_m, in thread order) inside an operand
-  // tile that holds tile_m <= kTile matrices (tile_m % kTileGran == 0)
+  // byte offset of record m (0 <= m < kTile, in thread order) inside an operand
+  // tile.  The layout is fixed by the CAPACITY of the tile: a tile that holds fewer
+  // matrices fills only the head of the buffer (of each segment when SEG), so the
+  // slots past its count land on unused bytes and never need a guard.
+  static constexpr int seg_stride(int len) { return bytes(len) / kSegs + kSegPad; }
   template <int LEN>
-  __device__ static __forceinline__ int rec_offset(int m, int tile_m) {
+  __device__ static __forceinline__ int rec_offset(int m) {
     if constexpr (SEG) {
-      const int seg_bytes = (tile_m >> 3) * LEN * int(sizeof(T));
-      return (m & (kSegs - 1)) * (seg_bytes + kSegPad) + (m >> 3) * LEN * int(sizeof(T));
+      return (m & (kSegs - 1)) * seg_stride(LEN) + (m >> 3) * LEN * int(sizeof(T));
     } else {
       return m * LEN * int(sizeof(T));
     }
@@ -112,14 +114,15 @@ __host__ __device__ inline int staged_mask(const KParams& p) {
   return m;
 }
 
-// element e (0 <= e < count*LEN, tile-global order) -> byte offset in the staged tile
+// element e (0 <= e < count*LEN, tile-global order of a FULL-capacity tile) -> byte
+// offset in the staged tile
 template <class G, int LEN>
-__device__ __forceinline__ int elem_offset(int e, int tile_m) {
+__device__ __forceinline__ int elem_offset(int e) {
   using T = typename G::T;
   if constexpr (G::kPad != 0) {
-    const int per_seg = (tile_m >> 3) * LEN;  // elements per segment
+    constexpr int per_seg = G::kTile / kSegs * LEN;  // elements per segment
     const int seg = e / per_seg;
-    return seg * (per_seg * int(sizeof(T)) + kSegPad) + (e - seg * per_seg) * int(sizeof(T));
+    return seg * G::seg_stride(LEN) + (e - seg * per_seg) * int(sizeof(T));
   } else {
     return e * int(sizeof(T));
   }
@@ -129,8 +132,7 @@ __device__ __forceinline__ int elem_offset(int e, int tile_m) {
 // `count` records between global memory and the staged layout with plain
 // coalesced accesses
 template <class G, int LEN>
-__device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typename G::T* src, int count, int tile_m, int idx,
-                                          int step) {
+__device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typename G::T* src, int count, int idx, int step) {
   using T = typename G::T;
   constexpr int U = 4;  // independent loads in flight per thread
   const int total = count * LEN;
@@ -140,16 +142,15 @@ __device__ __forceinline__ void coop_load(unsigned char* smem_tile, const typena
     for (int u = 0; u < U; ++u) v[u] = (e0 + u * step < total) ? src[e0 + u * step] : T(0);
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (e0 + u * step < total) *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e0 + u * step, tile_m)) = v[u];
+      if (e0 + u * step < total) *reinterpret_cast<T*>(smem_tile + elem_offset<G, LEN>(e0 + u * step)) = v[u];
   }
 }
 
 template <class G, int LEN>
-__device__ __forceinline__ void coop_store(typename G::T* dst, const unsigned char* smem_tile, int count, int tile_m, int idx,
-                                           int step) {
+__device__ __forceinline__ void coop_store(typename G::T* dst, const unsigned char* smem_tile, int count, int idx, int step) {
   using T = typename G::T;
   const int total = count * LEN;
-  for (int e = idx; e < total; e += step) dst[e] = *reinterpret_cast<const T*>(smem_tile + elem_offset<G, LEN>(e, tile_m));
+  for (int e = idx; e < total; e += step) dst[e] = *reinterpret_cast<const T*>(smem_tile + elem_offset<G, LEN>(e));
 }
 
 #ifdef NFM_TIMELINE
@@ -192,17 +193,15 @@ __global__ void __launch_bounds__(THREADS)
   //   ntiles tiles of tile_m <= THREADS*MPT matrices (tile_m % kTileGran == 0),
   //   one partial tile of part_m < tile_m matrices (part_m % TileGeom::kGran == 0,
   //     so it still moves by TMA, just with a smaller byte count), and
-  //   tail = p.batch - ntiles*tile_m - part_m < kGran matrices that cannot keep the
-  //     16-byte granularity of bulk copies: the last CTA does them straight from
-  //     global memory while its first tiles are in flight.
+  //   (the launcher hands the last p.batch % kGran matrices, which cannot keep the
+  //   16-byte granularity of bulk copies, to a second tiny launch of strided_kernel:
+  //   in this kernel that code cost the main loop 2-3 %).
   using T = typename Op::scalar;
   using G = TileGeom<Op, THREADS, MPT, SEG>;
   NFM_STAMP(0);
   const i64 ntiles_all = ntiles + (part_m > 0 ? 1 : 0);
-  const int tail = int(p.batch - ntiles * tile_m - part_m);
   constexpr int kIssuers = SEG ? kSegs : 1;  // threads that issue bulk copies (one segment each)
   constexpr int nseg = SEG ? kSegs : 1;
-  constexpr int pad = SEG ? kSegPad : 0;
   constexpr int es = int(sizeof(T));
   // L2 evict_first on the loads only for ops that write at least as much as they read
   constexpr bool kHint = Op::kOut >= ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0);
@@ -266,21 +265,21 @@ __global__ void __launch_bounds__(THREADS)
     const i64 first = tile * tile_m;
     const int per_seg = count_of(tile) / nseg;  // matrices per segment (per tile when !SEG)
     if (tid == 0) mbar_arrive_expect_tx(&full[stage], uint32_t(per_seg * nseg * staged_len * es));
-    const int seg = SEG ? tid : 0;
+    const int seg = SEG ? tid : 0;  // segment `seg` lands at its fixed (capacity) offset
     if (staged & 1) {
       const int sb = per_seg * Op::kLen0 * es;
-      bulk_g2s<kHint>(dst + seg * (sb + pad), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb, sb,
-                      &full[stage], policy);
+      bulk_g2s<kHint>(dst + seg * G::seg_stride(Op::kLen0), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb,
+                      sb, &full[stage], policy);
     }
     if (staged & 2) {
       const int sb = per_seg * Op::kLen1 * es;
-      bulk_g2s<kHint>(dst + f0 + seg * (sb + pad), reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb, sb,
-                      &full[stage], policy);
+      bulk_g2s<kHint>(dst + f0 + seg * G::seg_stride(Op::kLen1),
+                      reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb, sb, &full[stage], policy);
     }
     if (staged & 4) {
       const int sb = per_seg * Op::kLen2 * es;
-      bulk_g2s<kHint>(dst + f0 + f1 + seg * (sb + pad), reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb,
-                      sb, &full[stage], policy);
+      bulk_g2s<kHint>(dst + f0 + f1 + seg * G::seg_stride(Op::kLen2),
+                      reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb, sb, &full[stage], policy);
     }
   };
 
@@ -290,20 +289,6 @@ __global__ void __launch_bounds__(THREADS)
       const i64 t = i64(blockIdx.x) + i64(s) * gridDim.x;
       if (t < ntiles_all) issue(s, t);
     }
-  }
-
-  // the few matrices past the last 16-byte granule: straight from global memory
-  if (tail > 0 && blockIdx.x == gridDim.x - 1 && tid < tail) {
-    const i64 b = p.batch - tail + tid;
-    T r0[Op::kLen0], r1[Op::kLen1], r2[Op::kLen2], o[Op::kOut];
-    zero_record(r0);
-    zero_record(r1);
-    zero_record(r2);
-    if (p.present & 1) load_record_scalar(g0 + b * p.in[0].stride, r0);
-    if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1);
-    if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2);
-    apply_op<Op>(p, r0, r1, r2, o);
-    store_record_scalar(gout + b * Op::kOut, o);
   }
 
   int it = 0;
@@ -327,13 +312,13 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       const int m = tid + j * THREADS;
-      if (staged & 1) load_record(reinterpret_cast<const T*>(sin + G::template rec_offset<Op::kLen0>(m, cnt)), r0[j]);
+      if (staged & 1) load_record(reinterpret_cast<const T*>(sin + G::template rec_offset<Op::kLen0>(m)), r0[j]);
       else if (p.present & 1) load_record_scalar(g0, r0[j]);
       else zero_record(r0[j]);
-      if (staged & 2) load_record(reinterpret_cast<const T*>(sin + f0 + G::template rec_offset<Op::kLen1>(m, cnt)), r1[j]);
+      if (staged & 2) load_record(reinterpret_cast<const T*>(sin + f0 + G::template rec_offset<Op::kLen1>(m)), r1[j]);
       else if (p.present & 2) load_record_scalar(g1, r1[j]);
       else zero_record(r1[j]);
-      if (staged & 4) load_record(reinterpret_cast<const T*>(sin + f0 + f1 + G::template rec_offset<Op::kLen2>(m, cnt)), r2[j]);
+      if (staged & 4) load_record(reinterpret_cast<const T*>(sin + f0 + f1 + G::template rec_offset<Op::kLen2>(m)), r2[j]);
       else if (p.present & 4) load_record_scalar(g2, r2[j]);
       else zero_record(r2[j]);
     }
@@ -351,20 +336,23 @@ __global__ void __launch_bounds__(THREADS)
     for (int j = 0; j < MPT; ++j) {
       T o[Op::kOut];
       apply_op<Op>(p, r0[j], r1[j], r2[j], o);
-      // (in the SEG layout a slot beyond cnt would land on the next segment's first record)
-      const int m = tid + j * THREADS;
-      if (m < cnt) store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(m, cnt)), o);
+      store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(tid + j * THREADS)), o);
     }
     fence_proxy_async();
     __syncthreads();
     if (tid < kIssuers) {
       const int seg = SEG ? tid : 0;
       const int sbo = (cnt / nseg) * Op::kOut * es;
-      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * tile_m * Op::kOut) + seg * sbo, sout + seg * (sbo + pad), sbo);
+      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * tile_m * Op::kOut) + seg * sbo, sout + seg * G::seg_stride(Op::kOut),
+               sbo);
       bulk_commit();
     }
   }
+#ifdef NFM_AB_FINALWAIT
+  if (tid < kIssuers) bulk_wait<0>();
+#else
   if (tid < kIssuers) bulk_wait_read<0>();  // writes complete with the grid; only shared memory must outlive them
+#endif
   NFM_STAMP(3);
 #ifdef NFM_TIMELINE
   NFM_STAMP_VAL(4, smid());
@@ -415,7 +403,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
   constexpr int WT = PG::kWarpTile;
   constexpr int kIssuers = SEG ? kSegs : 1;
   constexpr int nseg = SEG ? kSegs : 1;
-  constexpr int pad = SEG ? kSegPad : 0;
   constexpr bool kHint = Op::kOut >= ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0);
   NFM_STAMP(0);
 
@@ -474,13 +461,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     if (lane == 0) mbar_arrive_expect_tx(&full[b], tx_bytes);
     const int seg = SEG ? lane : 0;
     if (staged & 1)
-      bulk_g2s<kHint>(dst + seg * (sb0 + pad), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb0, sb0,
-                      &full[b], policy);
+      bulk_g2s<kHint>(dst + seg * G::seg_stride(Op::kLen0), reinterpret_cast<const unsigned char*>(g0 + first * Op::kLen0) + seg * sb0,
+                      sb0, &full[b], policy);
     if (staged & 2)
-      bulk_g2s<kHint>(dst + f0 + seg * (sb1 + pad), reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb1,
-                      sb1, &full[b], policy);
+      bulk_g2s<kHint>(dst + f0 + seg * G::seg_stride(Op::kLen1),
+                      reinterpret_cast<const unsigned char*>(g1 + first * Op::kLen1) + seg * sb1, sb1, &full[b], policy);
     if (staged & 4)
-      bulk_g2s<kHint>(dst + f0 + f1 + seg * (sb2 + pad),
+      bulk_g2s<kHint>(dst + f0 + f1 + seg * G::seg_stride(Op::kLen2),
                       reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb2, sb2, &full[b], policy);
   };
 
@@ -512,9 +499,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #endif
     } else {
       const i64 first = tile * WT;
-      if (staged & 1) coop_load<G, Op::kLen0>(sbuf, g0 + first * Op::kLen0, rem, WT, lane, 32);
-      if (staged & 2) coop_load<G, Op::kLen1>(sbuf + f0, g1 + first * Op::kLen1, rem, WT, lane, 32);
-      if (staged & 4) coop_load<G, Op::kLen2>(sbuf + f0 + f1, g2 + first * Op::kLen2, rem, WT, lane, 32);
+      if (staged & 1) coop_load<G, Op::kLen0>(sbuf, g0 + first * Op::kLen0, rem, lane, 32);
+      if (staged & 2) coop_load<G, Op::kLen1>(sbuf + f0, g1 + first * Op::kLen1, rem, lane, 32);
+      if (staged & 4) coop_load<G, Op::kLen2>(sbuf + f0 + f1, g2 + first * Op::kLen2, rem, lane, 32);
       __syncwarp();
     }
 
@@ -522,13 +509,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       const int m = lane + j * 32;
-      if (staged & 1) load_record(reinterpret_cast<const T*>(sbuf + G::template rec_offset<Op::kLen0>(m, WT)), r0[j]);
+      if (staged & 1) load_record(reinterpret_cast<const T*>(sbuf + G::template rec_offset<Op::kLen0>(m)), r0[j]);
       else if (p.present & 1) load_record_scalar(g0, r0[j]);
       else zero_record(r0[j]);
-      if (staged & 2) load_record(reinterpret_cast<const T*>(sbuf + f0 + G::template rec_offset<Op::kLen1>(m, WT)), r1[j]);
+      if (staged & 2) load_record(reinterpret_cast<const T*>(sbuf + f0 + G::template rec_offset<Op::kLen1>(m)), r1[j]);
       else if (p.present & 2) load_record_scalar(g1, r1[j]);
       else zero_record(r1[j]);
-      if (staged & 4) load_record(reinterpret_cast<const T*>(sbuf + f0 + f1 + G::template rec_offset<Op::kLen2>(m, WT)), r2[j]);
+      if (staged & 4) load_record(reinterpret_cast<const T*>(sbuf + f0 + f1 + G::template rec_offset<Op::kLen2>(m)), r2[j]);
       else if (p.present & 4) load_record_scalar(g2, r2[j]);
       else zero_record(r2[j]);
     }
@@ -538,11 +525,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     for (int j = 0; j < MPT; ++j) {
       T o[Op::kOut];
       apply_op<Op>(p, r0[j], r1[j], r2[j], o);
-      store_record(reinterpret_cast<T*>(sbuf + G::template rec_offset<Op::kOut>(lane + j * 32, WT)), o);
+      store_record(reinterpret_cast<T*>(sbuf + G::template rec_offset<Op::kOut>(lane + j * 32)), o);
     }
     if (ragged) {
       __syncwarp();
-      coop_store<G, Op::kOut>(gout + tile * WT * Op::kOut, sbuf, rem, WT, lane, 32);
+      coop_store<G, Op::kOut>(gout + tile * WT * Op::kOut, sbuf, rem, lane, 32);
       break;
     }
     fence_proxy_async();
@@ -550,7 +537,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
     const i64 nxt = tile + i64(NBUF) * gridDim.x;  // next user of this buffer
     if (lane < kIssuers) {
       const int seg = SEG ? lane : 0;
-      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * WT * Op::kOut) + seg * sbo, sbuf + seg * (sbo + pad), sbo);
+      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * WT * Op::kOut) + seg * sbo, sbuf + seg * G::seg_stride(Op::kOut), sbo);
       bulk_commit();
       if (nxt < ntiles_all) bulk_wait_read<0>();  // the store has read the buffer: it can be refilled
     }
@@ -646,7 +633,9 @@ constexpr int pick_tile(int stages, int in_bytes, int out_bytes) {
   return 64;
 }
 
-constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile; }  // one matrix per thread up to 512; MPT <= 8
+// one matrix per thread up to 512 threads; MPT <= 8.  (1024 x 1 was re-measured in round 2
+// with the L2 prefetch: 118.2 vs 114.5 us for the 3x3 solve, profiles/r2_geometry_sweep.txt)
+constexpr int pick_threads(int tile) { return tile >= 1024 ? 512 : tile == 768 ? 384 : tile; }
 
 // Compute-heavy ops (pivoted elimination, Gauss-Jordan: Op::kHeavy) are bound by
 // the latency of their dependent chains rather than by HBM alone; they do best
@@ -669,7 +658,13 @@ struct TuneRule : TuneBase<Op> {
 #ifdef NFM_TUNE_TILE
   static constexpr int kTile = NFM_TUNE_TILE;
 #else
-  static constexpr int kTile = Op::kHeavy ? heavy_tile(B::kInBytes, B::kOutBytes) : pick_tile(kStages, B::kInBytes, B::kOutBytes);
+  // light ops that move >= 250 B per matrix (10x10 packed solve ...) carry ~150 registers per
+  // thread: three 128-matrix CTAs per SM beat one of 256 (7031 vs 6751 GB/s, r2_geometry_sweep)
+  static constexpr int kTile = Op::kHeavy                             ? heavy_tile(B::kInBytes, B::kOutBytes)
+                               : (B::kInBytes + B::kOutBytes >= 250) ? (pick_tile(kStages, B::kInBytes, B::kOutBytes) < 128
+                                                                            ? pick_tile(kStages, B::kInBytes, B::kOutBytes)
+                                                                            : 128)
+                                                                      : pick_tile(kStages, B::kInBytes, B::kOutBytes);
 #endif
 #ifdef NFM_TUNE_THREADS
   static constexpr int kThreads = NFM_TUNE_THREADS < kTile ? NFM_TUNE_THREADS : kTile;
@@ -692,52 +687,49 @@ struct TuneFixed : TuneBase<Op> {
 template <class Op>
 struct Tune : TuneRule<Op> {};
 
-// Second, smaller geometry for light ops with small records when a launch has
-// only a few tiles per CTA (mid-size batches: a multi-GPU slab, config 1).
-// Measured for the 3x3 fp32 solve (tune_main "small"): 512-matrix tiles beat
-// 1024 by 10 / 6 / 3.5 % at 0.5M / 1M / 2M matrices and lose by 3 % at 4M.
+// Second, smaller geometry for light ops when a launch is small (a multi-GPU slab,
+// config 1): several small CTAs per SM ramp up and drain faster than one big one.
+// Measured with the L2 prefetch in place (profiles/r2_geometry_sweep.txt):
+//   records <= 64 B  (3x3 solve): 256 threads x 2, 2 stages -- 8.4 vs 10.4 us at 1M,
+//       15.7 vs 18.2 us at 2M, 31.0 vs 32.9 us at 4M, equal at 8M matrices
+//   records <= 200 B (6x6 solve / invert): 128 threads x 1, 3 stages -- 18.2 vs 19.3 us and
+//       24.9 vs 25.4 us at 885k matrices, behind the large geometry from ~1.5M
+// `kBelowBytes`: use it when the launch moves fewer algorithmic bytes than this.
 template <class Op>
 struct TuneSmall {
   using B = TuneBase<Op>;
-  static constexpr bool kEnabled = !Op::kHeavy && (B::kInBytes + B::kOutBytes <= 64) && Tune<Op>::kTile >= 1024;
-  static constexpr int kThreads = 256, kMpt = 2, kStages = 3;
-  static constexpr int kTilesPerCtaBelow = 20;  // use it when the big geometry would give fewer tiles per SM than this
+  static constexpr int kRec = B::kInBytes + B::kOutBytes;
+  static constexpr bool kTiny = kRec <= 64;
+  static constexpr bool kEnabled = !Op::kHeavy && ((kTiny && Tune<Op>::kTile >= 1024) || (!kTiny && kRec <= 200 && Tune<Op>::kTile > 128));
+  static constexpr int kThreads = kTiny ? 256 : 128, kMpt = kTiny ? 2 : 1, kStages = kTiny ? 2 : 3;
+  static constexpr long long kBelowBytes = kTiny ? (400ll << 20) : (180ll << 20);
 };
 
 // Pool geometry for compute-heavy ops with large records (pool_kernel).
 // Measured on B200 (profiles/r2_pool_sweep.txt): the pool wins from ~256 B of
 // input per matrix (fp64 8x8 inverse 0.43 -> 0.86 of the measured peak, fp32
 // 10x10 0.66 -> 0.93) and loses below (4x4 fp64 inverse 0.90 vs 0.95).
-//   kMaxW : register budget (launch bounds) from the scalars a thread keeps live
-//           (Op::kLive when the op expands its record, else its input record)
-//   warps / buffers at run time: as many warps as that budget allows while
-//           ~1/4 of the pool (at least 2 buffers, at most ~80 KB) stays in flight.
-template <class Op, class = void>
-struct live_scalars { static constexpr int value = ((Op::kUse & 1) ? Op::kLen0 : 0) + ((Op::kUse & 2) ? Op::kLen1 : 0); };
-template <class Op>
-struct live_scalars<Op, std::void_t<decltype(Op::kLive)>> { static constexpr int value = Op::kLive; };
-
+//   kMaxW : register budget (launch bounds): 8 warps (255 registers) for fp64, 12 (168) for fp32
+//   warps / buffers at run time: kMaxW warps when shared memory holds that many
+//           buffers, plus 2-3 buffers in flight.  Larger pools were SLOWER (r2_pool_sweep:
+//           6x6 fp64 inverse 6550 GB/s with 8+2 buffers, 5735 with 12+12): the register
+//           spills of these kernels live in the L1 that a bigger pool takes away.
 template <class Op>
 struct PoolTune {
   using B = TuneBase<Op>;
-  static constexpr int kLiveWords = live_scalars<Op>::value * int(sizeof(typename Op::scalar)) / 4;
 #ifdef NFM_TUNE_POOL
   static constexpr bool kEnabled = NFM_TUNE_POOL && Op::kHeavy;
 #else
   static constexpr bool kEnabled = Op::kHeavy && B::kInBytes >= 256;
 #endif
-  static constexpr int kMaxW = kLiveWords <= 64 ? 16 : kLiveWords <= 112 ? 12 : 8;
+  static constexpr int kMaxW = sizeof(typename Op::scalar) == 8 ? 8 : 12;
   static constexpr int kMpt = 1;
   static void geometry(int buf_bytes, int max_smem, int& warps, int& nbuf) {
     int nbuf_max = (max_smem - 512) / (buf_bytes + 12);
-    if (nbuf_max > 24) nbuf_max = 24;
-    int flight = (80 * 1024 + buf_bytes - 1) / buf_bytes;
-    const int cap = nbuf_max / 4 > 2 ? nbuf_max / 4 : 2;
-    if (flight > cap) flight = cap;
-    if (flight < 2) flight = 2;
-    warps = nbuf_max - flight < kMaxW ? nbuf_max - flight : kMaxW;
+    warps = nbuf_max - 1 < kMaxW ? nbuf_max - 1 : kMaxW;
     if (warps < 1) warps = 1;
-    nbuf = nbuf_max < 3 * warps ? nbuf_max : 3 * warps;
+    const int flight = warps / 4 > 2 ? warps / 4 : 2;
+    nbuf = warps + flight < nbuf_max ? warps + flight : nbuf_max;
     if (nbuf <= warps) nbuf = warps + 1;
   }
 };
@@ -760,6 +752,21 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, si
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// the last few matrices of a dense batch (those past `done`), one thread each
+template <class Op>
+int launch_tail(const KParams& p, i64 done, cudaStream_t stream) {
+  using T = typename Op::scalar;
+  KParams q = p;
+  const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2};
+  for (int i = 0; i < kMaxIn; ++i)
+    if ((q.present >> i) & 1) q.in[i].ptr = static_cast<const T*>(q.in[i].ptr) + done * (q.in[i].stride == 0 ? 0 : lens[i]);
+  q.out = static_cast<T*>(q.out) + done * Op::kOut;
+  q.batch = p.batch - done;
+  cudaError_t e = launch_pdl(strided_kernel<Op>, 1u, 128u, size_t(0), stream, q);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(e);
 }
 
 // per (kernel instantiation, device, staged mask): resident CTAs per SM, 0 = not yet known
@@ -816,12 +823,18 @@ int launch_tile(const KParams& p, cudaStream_t stream) {
   const int tile_m = balance_enabled() ? balanced_tile(p.batch, grid_max, G::kTile) : G::kTile;
   const i64 ntiles = p.batch / tile_m;
   const int part_m = int(p.batch - ntiles * tile_m) / G::kGran * G::kGran;
-  i64 ntiles_all = ntiles + (part_m > 0 ? 1 : 0);
-  if (ntiles_all == 0) ntiles_all = 1;  // only a direct tail
-  const i64 grid = grid_max < ntiles_all ? grid_max : ntiles_all;
-  cudaError_t e = launch_pdl(kern, unsigned(grid), THREADS, size_t(smem), stream, p, ntiles, tile_m, part_m);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return int(e);
+  const i64 ntiles_all = ntiles + (part_m > 0 ? 1 : 0);
+  const i64 covered = ntiles * tile_m + part_m;
+  if (ntiles_all > 0) {
+    KParams q = p;
+    q.batch = covered;
+    const i64 grid = grid_max < ntiles_all ? grid_max : ntiles_all;
+    cudaError_t e = launch_pdl(kern, unsigned(grid), THREADS, size_t(smem), stream, q, ntiles, tile_m, part_m);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return int(e);
+  }
+  if (covered < p.batch) return launch_tail<Op>(p, covered, stream);  // < kGran matrices
+  return 0;
 }
 
 template <class Op, int MAXW, int MPT, bool SEG>
@@ -897,7 +910,7 @@ int run_op(KParams p, cudaStream_t stream) {
       rc = launch_pool<Op, Pt::kMaxW, Pt::kMpt, Tn::kSeg>(p, warps, nbuf, stream);
     } else {
     bool small = false;
-    if constexpr (TuneSmall<Op>::kEnabled) small = p.batch / TILE < i64(TuneSmall<Op>::kTilesPerCtaBelow) * device_info().sm_count;
+    if constexpr (TuneSmall<Op>::kEnabled) small = p.batch * TuneSmall<Op>::kRec < TuneSmall<Op>::kBelowBytes;
     if constexpr (TuneSmall<Op>::kEnabled) {
       using Ts = TuneSmall<Op>;
       rc = small ? launch_tile<Op, Ts::kThreads, Ts::kMpt, Ts::kStages, Tn::kSeg>(p, stream)

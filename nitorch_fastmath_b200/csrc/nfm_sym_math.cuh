@@ -323,7 +323,7 @@ struct GaussPP {
           p = i;
         }
       });
-      if (warp_any(p != k)) {  // skipped when no matrix of the warp exchanges rows in this step
+      if (N < kVoteFromOrder || warp_any(p != k)) {  // skipped when no matrix of the warp exchanges rows in this step
         static_for<k + 1, N>([&](auto I) {
           constexpr int i = I;
           const bool sw = (p == i);

@@ -63,7 +63,6 @@ struct SymSolveOp {
   static constexpr int kUse = 7;
   static constexpr int kOut = N;
   static constexpr bool kHeavy = (LAYOUT == NFM_LAYOUT_SYM && N > 4 && ALGO == NFM_ALGO_LU) || (LAYOUT == NFM_LAYOUT_FULL && N >= 2);
-  static constexpr int kLive = (LAYOUT == NFM_LAYOUT_SYM && N > 4 && ALGO != NFM_ALGO_LDL) ? N * N + N : kLen0 + N;  // LU expands the packed record
 
   __device__ static __forceinline__ void apply(const T (&m_in)[kLen0], const T (&v)[N], const T (&reg)[N],
                                                int present, int flags, T (&x)[N]) {
@@ -159,7 +158,6 @@ struct SymInvertOp {
   static constexpr int kUse = 1;
   static constexpr int kOut = DIAG_ONLY ? N : packed_len(N);
   static constexpr bool kHeavy = N > 4 && ALGO == NFM_ALGO_LU;
-  static constexpr int kLive = (N > 4 && ALGO != NFM_ALGO_LDL) ? N * N : kLen0;  // Gauss-Jordan expands the packed record
 
   __device__ static __forceinline__ void apply(const T (&m)[kLen0], const T (&)[1], const T (&)[1], int present,
                                                int flags, T (&out)[kOut]) {

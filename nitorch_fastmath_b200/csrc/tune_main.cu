@@ -117,7 +117,7 @@ void run_sliced(const char* name, const Buffers& b, int alg_bytes, i64 sub) {
   cudaEventCreate(&e1);
   for (int i = 0; i < slices; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i], 0);
   cudaDeviceSynchronize();
-  const int reps = 10 * slices;
+  const int reps = slices > 1 ? 10 * slices : 10;
   cudaEventRecord(e0);
   for (int i = 0; i < reps; ++i) launch_tile<Op, THREADS, MPT, STAGES, SEG>(ps[i % slices], 0);
   cudaEventRecord(e1);
@@ -256,6 +256,7 @@ int main(int argc, char** argv) {
     CFG(Op, "sym_solve3", 1024, 1, 3, false, 48);
     release(buf);
   }
+#ifndef NFM_TUNE_MIN
   if (want("small")) {
     using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
     Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
@@ -344,6 +345,82 @@ int main(int argc, char** argv) {
     g_balance = true;
     release(b10);
   }
+  // geometry sweep of the headline light ops over slab sizes (1, 1/2, 1/4, 1/8 of the config)
+#define GEO(OP, NAME, THR, MPT, ST, BYTES)                                  \
+  for (i64 sub : subs)                                                       \
+    if (size_t(ST) * THR * MPT * in_b + 2 * size_t(THR) * MPT * out_b <= 225 * 1024) \
+      run_sliced<OP, THR, MPT, ST, false>(NAME, buf, BYTES, sub);
+#define GEOSET(OP, NAME, BYTES)                                                                      \
+  GEO(OP, NAME, 128, 1, 2, BYTES) GEO(OP, NAME, 128, 1, 3, BYTES) GEO(OP, NAME, 128, 1, 4, BYTES)    \
+  GEO(OP, NAME, 128, 2, 3, BYTES) GEO(OP, NAME, 128, 2, 4, BYTES) GEO(OP, NAME, 256, 1, 2, BYTES)    \
+  GEO(OP, NAME, 256, 1, 3, BYTES) GEO(OP, NAME, 256, 1, 4, BYTES) GEO(OP, NAME, 256, 2, 2, BYTES)    \
+  GEO(OP, NAME, 256, 2, 3, BYTES) GEO(OP, NAME, 256, 2, 4, BYTES) GEO(OP, NAME, 512, 1, 2, BYTES)    \
+  GEO(OP, NAME, 512, 1, 3, BYTES) GEO(OP, NAME, 512, 1, 4, BYTES) GEO(OP, NAME, 512, 2, 2, BYTES)    \
+  GEO(OP, NAME, 512, 2, 3, BYTES) GEO(OP, NAME, 768, 1, 3, BYTES) GEO(OP, NAME, 1024, 1, 2, BYTES)   \
+  GEO(OP, NAME, 1024, 1, 3, BYTES)
+  if (want("geo_solve3")) {
+    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
+    const i64 full = 256ll * 256 * 256;
+    Buffers buf = make<float>(full, 6, 3, 3, 3);
+    const i64 subs[] = {1000000, full / 8, full / 4, full / 2, full};
+    const size_t in_b = 36, out_b = 12;
+    GEOSET(Op, "solve3", 48)
+    release(buf);
+  }
+  if (want("geo_matvec3")) {
+    using Op = SymMatvecOp<float, 3, NFM_LAYOUT_SYM>;
+    const i64 full = 256ll * 256 * 256;
+    Buffers buf = make<float>(full, 6, 3, 3, 3);
+    const i64 subs[] = {1000000, full / 8, full};
+    const size_t in_b = 36, out_b = 12;
+    GEOSET(Op, "matvec3", 48)
+    release(buf);
+  }
+  if (want("geo_solve6")) {
+    using Op = SymSolveOp<float, 6, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    const i64 full = 192ll * 192 * 192;
+    Buffers buf = make<float>(full, 21, 6, 6, 6);
+    const i64 subs[] = {full / 8, full / 4, full / 2, full};
+    const size_t in_b = 108, out_b = 24;
+    GEOSET(Op, "solve6", 132)
+    release(buf);
+  }
+  if (want("geo_invert6")) {
+    using Op = SymInvertOp<float, 6, NFM_ALGO_AUTO, false>;
+    const i64 full = 192ll * 192 * 192;
+    Buffers buf = make<float>(full, 21, 6, 0, 21);
+    const i64 subs[] = {full / 8, full / 4, full / 2, full};
+    const size_t in_b = 84, out_b = 84;
+    GEOSET(Op, "invert6", 168)
+    release(buf);
+  }
+  if (want("geo_solve10")) {
+    using Op = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_AUTO>;
+    const i64 full = 160ll * 160 * 160;
+    Buffers buf = make<float>(full, 55, 10, 10, 10);
+    const i64 subs[] = {full / 8, full / 4, full / 2, full};
+    const size_t in_b = 260, out_b = 40;
+    GEOSET(Op, "solve10", 300)
+    release(buf);
+  }
+  if (want("geo_solve4")) {
+    using Op = SymSolveOp<float, 4, NFM_LAYOUT_SYM, 0>;
+    const i64 full = 1ll << 24;
+    Buffers buf = make<float>(full, 10, 4, 4, 4);
+    const i64 subs[] = {full / 8, full};
+    const size_t in_b = 56, out_b = 16;
+    GEOSET(Op, "solve4", 72)
+    release(buf);
+  }
+  if (want("geo_solve3d")) {
+    using Op = SymSolveOp<double, 3, NFM_LAYOUT_SYM, 0>;
+    const i64 full = 1ll << 24;
+    Buffers buf = make<double>(full, 6, 3, 3, 3);
+    const i64 subs[] = {full / 8, full};
+    const size_t in_b = 72, out_b = 24;
+    GEOSET(Op, "solve3 f64", 96)
+    release(buf);
+  }
 #define TILE_RULE(OP, NAME, BYTES) \
   run_config<OP, Tune<OP>::kThreads, Tune<OP>::kMpt, Tune<OP>::kStages, Tune<OP>::kSeg>(NAME " tile-rule", buf, BYTES)
 #define POOLBLOCK(TAG, OP, T, NAME, BATCH, L0, ND, L1, LO, BYTES) \
@@ -364,6 +441,18 @@ int main(int argc, char** argv) {
   using SolF10 = BatchSolveOp<float, 10, NFM_ALGO_LU>;
   using SymLuF10 = SymSolveOp<float, 10, NFM_LAYOUT_SYM, NFM_ALGO_LU>;
   using SymLuD10 = SymSolveOp<double, 10, NFM_LAYOUT_SYM, NFM_ALGO_LU>;
+  using InvD5 = BatchInvOp<double, 5, NFM_ALGO_AUTO>;
+  using InvD4 = BatchInvOp<double, 4, NFM_ALGO_AUTO>;
+  using InvF7 = BatchInvOp<float, 7, NFM_ALGO_AUTO>;
+  using InvF6 = BatchInvOp<float, 6, NFM_ALGO_AUTO>;
+  using InvF5 = BatchInvOp<float, 5, NFM_ALGO_AUTO>;
+  using SolD6 = BatchSolveOp<double, 6, NFM_ALGO_LU>;
+  POOLBLOCK("pool_inv5d", InvD5, double, "inv5 f64", 8ll << 20, 25, -5, 0, 25, 400)
+  POOLBLOCK("pool_inv4d", InvD4, double, "inv4 f64", 16ll << 20, 16, -4, 0, 16, 256)
+  POOLBLOCK("pool_inv7f", InvF7, float, "inv7 f32", 8ll << 20, 49, -7, 0, 49, 392)
+  POOLBLOCK("pool_inv6f", InvF6, float, "inv6 f32", 8ll << 20, 36, -6, 0, 36, 288)
+  POOLBLOCK("pool_inv5f", InvF5, float, "inv5 f32", 8ll << 20, 25, -5, 0, 25, 200)
+  POOLBLOCK("pool_solve6d", SolD6, double, "solve6 f64", 8ll << 20, 36, -6, 6, 6, 384)
   POOLBLOCK("pool_inv8d", InvD8, double, "inv8 f64", 4ll << 20, 64, -8, 0, 64, 1024)
   POOLBLOCK("pool_inv10d", InvD10, double, "inv10 f64", 4ll << 20, 100, -10, 0, 100, 1600)
   POOLBLOCK("pool_inv6d", InvD6, double, "inv6 f64", 8ll << 20, 36, -6, 0, 36, 576)
@@ -501,12 +590,21 @@ int main(int argc, char** argv) {
     CFG(Op, "sym_solve10 auto", 128, 1, 3, false, 300);
     release(buf);
   }
+#endif  // NFM_TUNE_MIN
   if (want("inv4d")) {
     using Op = BatchInvOp<double, 4, NFM_ALGO_AUTO>;
     Buffers buf = make<double>(16ll << 20, 16, -4, 0, 16);
     CFG(Op, "dense_inv4d", 256, 1, 3, true, 256);   // pinned (TuneFixed)
     CFG(Op, "dense_inv4d", 256, 1, 3, false, 256);  // dense layout: 8-way bank conflicts
     CFG(Op, "dense_inv4d", 128, 1, 3, true, 256);
+    release(buf);
+  }
+  if (want("det4d")) {
+    using Op = BatchDetOp<double, 4>;
+    Buffers buf = make<double>(16ll << 20, 16, -4, 0, 1);
+    CFG(Op, "dense_det4d", 128, 2, 3, true, 136);  // pinned
+    CFG(Op, "dense_det4d", 256, 1, 3, true, 136);
+    CFG(Op, "dense_det4d", 128, 1, 3, true, 136);
     release(buf);
   }
   if (want("solve4d")) {

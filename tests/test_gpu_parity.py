@@ -156,16 +156,19 @@ def test_dense_fast_path_vs_oracle(nfm, dtype, n):
 
 @pytest.mark.parametrize("batch", [1, 2, 63, 64, 1023, 1024, 1025, 2 * 1024 + 17, 148 * 1024 + 5])
 def test_ragged_tile_boundaries(nfm, batch):
-    """Batches around the tile size: full tiles go by TMA, the ragged remainder is
-    finished inside the same launch (cooperative copy) -- 3x3 fp32 (tile 1024),
-    6x6 fp32 (tile 512), dense 4x4 fp64 (segmented layout, tile 256)."""
+    """Batches around the tile size: full tiles go by TMA, and so does the partial
+    last tile (a smaller byte count); only the batch % 4 (% 32 in the segmented layout)
+    matrices that break the 16-byte granularity of bulk copies go to the strided
+    kernel -- 3x3 fp32 (tile 1024), 6x6 fp32 (tile 512), dense 4x4 fp64 (segmented)."""
     from nitorch_fastmath_b200 import _lib
     for n in (3, 6):
         mat = G.spd_packed(batch, n, torch.float32, seed=batch + n)
         vec = G.vectors(batch, n, torch.float32, seed=batch + n + 1)
         before = _lib.launch_count()
         x = nfm.sym_solve(mat.to(DEV), vec.to(DEV))
-        assert _lib.launch_count() - before == 1 and _lib.load().nfm_last_path_was_tma() == 1
+        # one launch; the < 4 matrices past the last 16-byte granule take a second, tiny one
+        assert _lib.launch_count() - before == (1 if batch % 4 == 0 or batch < 4 else 2)
+        assert _lib.load().nfm_last_path_was_tma() == 1
         close(x, P.sym_solve(mat, vec), torch.float32)
         close(nfm.sym_invert(mat.to(DEV)), P.sym_invert(mat), torch.float32)
     a = G.dense_shifted(batch, 4, torch.float64, seed=batch)
@@ -173,6 +176,62 @@ def test_ragged_tile_boundaries(nfm, batch):
     close(nfm.batchinv(a.to(DEV)), P.batchinv(a), torch.float64, 2)
     close(nfm.batchdet(a.to(DEV)), P.batchdet(a), torch.float64, 0)
     close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), torch.float64)
+
+
+def _row_permuted(a, seed):
+    """Every second matrix gets its rows shuffled: well conditioned, but partial
+    pivoting has to exchange rows -- in some lanes of a warp and not in others."""
+    g = G.gen(seed)
+    a = a.clone()
+    n = a.shape[-1]
+    for b in range(1, a.shape[0], 2):
+        a[b] = a[b][torch.randperm(n, generator=g)]
+    return a
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [4, 5, 6, 8, 10])
+def test_pivoting_differs_between_lanes_of_a_warp(nfm, dtype, n):
+    """The pivoted eliminations skip the row / column exchanges of a step when no
+    matrix of the warp needs them (warp vote).  Here half of the lanes need them."""
+    batch = 4771 if n >= 8 else 20011        # n >= 8: pool kernel (32-matrix warp tiles) + ragged tile
+    a = _row_permuted(G.dense_shifted(batch, n, dtype, seed=n), seed=100 + n)
+    b = G.vectors(batch, n, dtype, seed=30 + n)
+    da, db = a.to(DEV), b.to(DEV)
+    close(nfm.batchinv(da), P.batchinv(a), dtype, 2, scale=4)
+    close(nfm.batchdet(da), P.batchdet(a), dtype, 0, scale=4)
+    close(nfm.solvevec(da, db), P.solvevec(a, b), dtype, scale=4)
+    close(nfm.lmdiv(da, db[..., None].expand(-1, -1, 3).contiguous()),
+          P.lmdiv(a, b[..., None].expand(-1, -1, 3).contiguous()), dtype, 2, scale=4)
+    # unpermuted input in the same launch shape: no lane exchanges anything
+    a0 = G.dense_shifted(batch, n, dtype, seed=n)
+    close(nfm.batchinv(a0.to(DEV)), P.batchinv(a0), dtype, 2)
+    if n > 4:
+        # packed symmetric, method='lu': indefinite matrices pivot, SPD ones do not; interleave them
+        m = G.spd_packed(batch, n, dtype, seed=n)
+        mi = G.sym_indefinite_packed(batch, n, dtype, seed=n + 1)
+        m[1::2] = mi[1::2]
+        v = G.vectors(batch, n, dtype, seed=50 + n)
+        want = P.sym_solve(m, v)
+        close(nfm.sym_solve(m.to(DEV), v.to(DEV), method="lu"), want, dtype, scale=20)
+        close(nfm.sym_solve(m.to(DEV), v.to(DEV)), want, dtype, scale=20)
+        close(nfm.sym_invert(m.to(DEV), method="lu"), P.sym_invert(m), dtype, scale=20)
+
+
+@pytest.mark.parametrize("batch", [1, 31, 32, 33, 95, 32 * 148 + 5, 32 * 148 * 3 + 64])
+def test_pool_kernel_tile_boundaries(nfm, batch):
+    """Heavy ops with large records run on the warp-pool kernel (32-matrix warp
+    tiles, buffers handed from warp to warp): batches around the warp tile and
+    around one / several rounds of the pool."""
+    from nitorch_fastmath_b200 import _lib
+    for n, dtype in ((8, torch.float64), (10, torch.float32), (10, torch.float64)):
+        a = _row_permuted(G.dense_shifted(batch, n, dtype, seed=batch + n), seed=batch)
+        b = G.vectors(batch, n, dtype, seed=batch + 1)
+        x = nfm.batchinv(a.to(DEV))
+        assert _lib.load().nfm_last_path_was_tma() == 1
+        close(x, P.batchinv(a), dtype, 2, scale=4)
+        close(nfm.batchdet(a.to(DEV)), P.batchdet(a), dtype, 0, scale=4)
+        close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), dtype, scale=4)
 
 
 @pytest.mark.parametrize("batch", [1, 77, 1024, 1030, 5000])
@@ -216,13 +275,19 @@ def test_writes_stay_inside_the_output(nfm, batch):
                 torch.cuda.synchronize()
                 assert intact(buf, out.numel())
             assert torch.equal(mat, mat0) and torch.equal(vec, vec0)
-        for n in (2, 4, 8):                       # segmented layout
+        for n in (2, 4, 8, 10):                   # segmented layout; n >= 8: warp-pool kernel
             a = G.dense_shifted(batch, n, dtype, seed=n).to(DEV)
             b = G.vectors(batch, n, dtype, seed=n + 1).to(DEV)
+            a0 = a.clone()
             buf, out = guarded((batch, n), dtype)
             nfm.solvevec(a, b, out=out)
             torch.cuda.synchronize()
             assert intact(buf, out.numel()) and not bool((out == sentinel).any())
+            buf, out = guarded((batch, n, n), dtype)
+            nfm.inv(a, out=out)
+            torch.cuda.synchronize()
+            assert intact(buf, out.numel()) and not bool((out == sentinel).any())
+            assert torch.equal(a, a0)
 
 
 def test_back_to_back_launches_are_ordered(nfm):
