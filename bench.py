@@ -17,8 +17,9 @@ compact-symmetric solve in fp32 (16 777 216 matrices, 48 B each).
           slabs, one process per GPU, no data-path collective; torch.distributed
           is used only for the barrier and the max-over-ranks of the time.
 
-One JSON line on stdout (rank 0).  With --impl reference the reference's CPU
-algorithm (oracle/ref_port.py, kind "port") is timed on the host cores.
+One JSON line on stdout (rank 0).  With --impl reference the reference's own CPU
+implementation (unmodified, from baseline/_ref -- kind "reference"; the pinned
+oracle port only if it cannot be imported) is timed on the host cores.
 """
 from __future__ import annotations
 
@@ -162,29 +163,43 @@ def api_call(kind: str, ins, out):
     if kind == "sym_invert":
         return sym.sym_invert(ins[0], out=out)
     if kind == "batch_inv":
-        return batched.batchinv(ins[0])
+        return batched.batchinv(ins[0], out=out)
     if kind == "batch_det":
-        return batched.batchdet(ins[0])
+        return batched.batchdet(ins[0], out=out)
     if kind == "batch_solve":
-        return sugar.solvevec(ins[0], ins[1])
+        return sugar.solvevec(ins[0], ins[1], out=out)
     raise ValueError(kind)
+
+
+_REFERENCE = None
+
+
+def reference_impl():
+    """(kind label, module-like namespace of callables): the reference's OWN code when it
+    can be imported (baseline/_ref, installed by oracle/install_reference.py; or
+    /root/reference in the build container), else the oracle port."""
+    global _REFERENCE
+    if _REFERENCE is None:
+        try:
+            from oracle import load_reference as L
+            if not L.available():
+                raise RuntimeError("no reference install")
+            ref_sym, ref_batched, ref_sugar = L.load()
+            _REFERENCE = ("reference", {
+                "sym_solve": ref_sym.sym_solve, "sym_matvec": ref_sym.sym_matvec, "sym_invert": ref_sym.sym_invert,
+                "batch_inv": ref_batched.batchinv, "batch_det": ref_batched.batchdet, "batch_solve": ref_sugar.solvevec,
+            }, "nitorch_fastmath (unmodified, %s): _impl/sym.py, _impl/batched.py, sugar.py" % L.REFERENCE_ROOT)
+        except Exception as exc:  # noqa: BLE001 -- any import problem -> the pinned port
+            from oracle import ref_port as P
+            _REFERENCE = ("port", {
+                "sym_solve": P.sym_solve, "sym_matvec": P.sym_matvec, "sym_invert": P.sym_invert,
+                "batch_inv": P.batchinv, "batch_det": P.batchdet, "batch_solve": P.solvevec,
+            }, "oracle/ref_port.py = the reference's torch-CPU algorithm (reference not importable: %s)" % exc)
+    return _REFERENCE
 
 
 def oracle_call(kind: str, ins):
-    from oracle import ref_port as P
-    if kind == "sym_solve":
-        return P.sym_solve(ins[0], ins[1])
-    if kind == "sym_matvec":
-        return P.sym_matvec(ins[0], ins[1])
-    if kind == "sym_invert":
-        return P.sym_invert(ins[0])
-    if kind == "batch_inv":
-        return P.batchinv(ins[0])
-    if kind == "batch_det":
-        return P.batchdet(ins[0])
-    if kind == "batch_solve":
-        return P.solvevec(ins[0], ins[1])
-    raise ValueError(kind)
+    return reference_impl()[1][kind](*ins)
 
 
 def bind_to_gpu_cpus(index: int):
@@ -276,8 +291,8 @@ def cpu_model() -> str:
 
 
 def cpu_baseline(kind, n, dtype, batch, steps=3, warmup=1, budget_s=20.0):
-    """The reference's CPU algorithm (oracle port, torch CPU ops exactly as the
-    reference issues them) on all host cores, on a bounded sample of the
+    """The reference's CPU implementation (its own code from baseline/_ref when
+    importable, else the pinned oracle port) on all host cores, on a bounded sample of the
     workload: the sample is sized from a calibration run so that
     (warmup + steps) passes take about ``budget_s`` seconds."""
     cores = os.cpu_count() or 1
@@ -312,10 +327,9 @@ def cpu_baseline(kind, n, dtype, batch, steps=3, warmup=1, budget_s=20.0):
         single = small[0].shape[0] / (time.perf_counter() - t0)
     finally:
         torch.set_num_threads(cores)
-    return {"value": sample / mean, "unit": "matrices/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": sample / mean, "unit": "matrices/s", "cores": torch.get_num_threads(), "kind": reference_impl()[0],
             "cpu_model": cpu_model(), "single_thread_value": single,
-            "sample": f"{sample} of {batch} matrices per step, {steps} steps after {warmup} warm-up; "
-                      "oracle/ref_port.py = the reference's torch-CPU algorithm",
+            "sample": f"{sample} of {batch} matrices per step, {steps} steps after {warmup} warm-up; " + reference_impl()[2],
             "best_value": sample / min(times), "seconds_per_step": mean, "sample_matrices": sample}
 
 
@@ -356,7 +370,10 @@ def main():
     esize = 4 if dtype == torch.float32 else 8
     batch = args.batch or w["batch"]
     alg = algorithmic_bytes(kind, n, esize)
-    config = {"workload": w["desc"], "routine": kind, "n": n, "batch": batch, "bytes_per_matrix": alg, "method": args.method}
+    # the same keys and values in both arms (the driver compares them)
+    config = {"workload": w["desc"], "routine": kind, "n": n, "batch": batch, "bytes_per_matrix": alg, "method": args.method,
+              "l2": "working set per GPU larger than L2, or >= 3x L2 of rotated operand sets (see timing.l2)"}
+    timing = {}
 
     if args.impl == "reference":
         if rank != 0:
@@ -380,7 +397,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1 and os.environ.get("NFM_BENCH_BIND") == "1":   # optional: measured no gain on this pool's hosts
-        config["cpu_affinity"] = bind_to_gpu_cpus(local_rank)
+        timing["cpu_affinity"] = bind_to_gpu_cpus(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -400,7 +417,7 @@ def main():
         ins = make_inputs(kind, n, dtype, my, dev, seed=1000 * rank + s)
         out = torch.empty(my, olen, device=dev, dtype=dtype) if olen > 1 else torch.empty(my, device=dev, dtype=dtype)
         sets.append((ins, out))
-    config["l2"] = (f"per-GPU working set {set_bytes / 2**20:.0f} MiB > L2" if nsets == 1 else
+    timing["l2"] = (f"per-GPU working set {set_bytes / 2**20:.0f} MiB > L2" if nsets == 1 else
                     f"rotating {nsets} operand sets of {set_bytes / 2**20:.0f} MiB (> 3x L2 in total)")
 
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -441,18 +458,29 @@ def main():
     peak, peak_src = measured_peak()
     local_ms = ev0.elapsed_time(ev1) / args.steps
     achieved = my * alg / (local_ms * 1e-3) / 1e9
+    path = int(lib.nfm_last_path_was_tma())
+    kernel = {1: "nfm::tile_kernel", 2: "nfm::warp_solve_kernel", 3: "nfm::pool_kernel", 0: "nfm::strided_kernel"}[path]
+    # dram bytes per launch come from a committed ncu capture of the default single-GPU run of this
+    # workload (profiles/traffic.json): a lookup, not a measurement of this run -- null otherwise
+    default_run = world == 1 and args.method == "auto" and batch == WORKLOADS[args.workload]["batch"] and not (args.kind or args.n or args.dtype)
+    traffic = recorded_traffic(args.workload) if default_run else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
-                "frac_of_nominal_8TBs": achieved / 8000.0,
-                "kernel": "nfm::tile_kernel<%s n=%d %s> (1 launch per step per GPU, TMA-staged)" % (kind, n, w["dtype"]),
+                "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload at 1 GPU; not measured in this run)" if traffic else None,
+                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "kernel": "%s<%s n=%d %s> (%d launch(es) per step per GPU, TMA-staged)" % (kernel, kind, n, w["dtype"], launches // max(args.steps, 1)),
                 "bytes_per_launch": my * alg, "avg_launch_us": local_ms * 1e3}
 
     # end to end: host (pinned) operands through the public API
     e2e = None
-    if not args.no_e2e and kind.startswith("sym"):
+    if not args.no_e2e:
         ins0, _ = sets[0]
-        host_in = [t.cpu().pin_memory() for t in ins0]
-        host_out = torch.empty((my, olen), dtype=dtype).pin_memory()
+        # a bounded slab for the 17 GB dense workloads: the e2e rate is set by PCIe, not by the size
+        e2e_n = min(my, max(1 << 20, int(2e9) // alg))
+        host_in = [t[:e2e_n].cpu().pin_memory() for t in ins0]
+        host_out = (torch.empty((e2e_n, olen), dtype=dtype) if olen > 1 else torch.empty((e2e_n,), dtype=dtype)).pin_memory()
+        if kind == "batch_inv":
+            host_out = host_out.view(e2e_n, n, n)
         ksteps = args.e2e_steps or max(3, min(args.steps, 10))
         for _ in range(2):
             api_call(kind, host_in, host_out)
@@ -466,11 +494,11 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": batch / (dt / ksteps), "unit": "matrices/s",
+        e2e = {"value": e2e_n * world / (dt / ksteps), "unit": "matrices/s",
                "h2d_bytes_per_step": sum(t.numel() * esize for t in host_in) * world,
                "d2h_bytes_per_step": host_out.numel() * esize * world, "steps": ksteps,
-               "ms_per_step": dt / ksteps * 1e3,
-               "api": "nitorch_fastmath_b200.sym.%s(pinned CPU tensors, out=pinned CPU tensor)" % kind}
+               "ms_per_step": dt / ksteps * 1e3, "matrices_per_step": e2e_n * world,
+               "api": "nitorch_fastmath_b200 %s(pinned CPU tensors%s)" % (kind, ", out=pinned CPU tensor")}
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -480,7 +508,7 @@ def main():
         line = {"metric": "batched sym-solve matrices/sec" if kind == "sym_solve" else f"{kind} matrices/sec",
                 "value": value, "unit": "matrices/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": w["dtype"], "data": "synthetic", "config": config, "roofline": roofline,
+                "dtype": w["dtype"], "data": "synthetic", "config": config, "timing": timing, "roofline": roofline,
                 "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e}
         if base is not None:
             line["cpu_baseline"] = base

@@ -71,7 +71,9 @@ const char *nfm_last_error_string(void);
 /* number of kernel launches issued by this library in the calling process */
 uint64_t nfm_launch_count(void);
 /* 1 if the last call on this thread used the TMA-staged thread-per-matrix fast
- * path for its bulk, 2 if it used the sub-warp cooperative kernel, 0 otherwise */
+ * path for its bulk (tile kernel), 2 if it used the sub-warp cooperative kernel,
+ * 3 if it used the TMA-staged warp-pool kernel (pivoted ops on large records),
+ * 0 otherwise (strided kernel) */
 int nfm_last_path_was_tma(void);
 
 /* y = A v            (inp == NULL, sign ignored)
@@ -232,6 +234,23 @@ int nfm_sym_matvec_host(int dtype, int n, int64_t batch,
                         const void *h_inp, int sign, void *h_out,
                         void *d_workspace, size_t workspace_bytes,
                         int64_t chunk, int nbuf, void **streams);
+
+/* Dense routines with HOST operands, same pipeline: batchinv / batchdet
+ * (_impl/batched.py:35-130) and lmdiv / solvevec (sugar.py:75-137, :290-341)
+ * called on CPU tensors.  a: n x n row-major records; b, out of the solve:
+ * n x nrhs row-major records; out of det: one scalar per matrix. */
+int nfm_batch_inv_host(int dtype, int n, int algo, int closed_form_reg, int64_t batch,
+                       const void *h_a, void *h_out,
+                       void *d_workspace, size_t workspace_bytes,
+                       int64_t chunk, int nbuf, void **streams);
+int nfm_batch_det_host(int dtype, int n, int64_t batch,
+                       const void *h_a, void *h_out,
+                       void *d_workspace, size_t workspace_bytes,
+                       int64_t chunk, int nbuf, void **streams);
+int nfm_batch_solve_host(int dtype, int n, int nrhs, int algo, int64_t batch,
+                         const void *h_a, const void *h_b, void *h_out,
+                         void *d_workspace, size_t workspace_bytes,
+                         int64_t chunk, int nbuf, void **streams);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ class _DeviceState:
         self.streams = [torch.cuda.Stream(device=device) for _ in range(_NBUF)]
         self.stream_array = (ctypes.c_void_p * _NBUF)(*[s.cuda_stream for s in self.streams])
         self.workspace: Optional[torch.Tensor] = None
+        self.lock = threading.Lock()   # one pipeline at a time per device: workspace and streams are shared
 
     def ensure_workspace(self, nbytes: int) -> torch.Tensor:
         if self.workspace is None or self.workspace.numel() < nbytes:
@@ -76,7 +77,7 @@ def run_host(fn_name: str, dtype_code: int, dtype: torch.dtype, in_elems: int, o
         chunk = chunk_for(dtype, in_elems, out_elems)
     chunk = max(1, min(chunk, max(batch, 1)))
     nbytes = int(lib.nfm_host_workspace_bytes(dtype_code, chunk, _NBUF, in_elems, out_elems))
-    with torch.cuda.device(dev):
+    with st.lock, torch.cuda.device(dev):
         ws = st.ensure_workspace(nbytes)
         # the pipeline streams must not start before pending work on the current stream
         cur = torch.cuda.current_stream(dev)

@@ -53,6 +53,9 @@ SIGNATURES = {
     "nfm_sym_solve_host": (c_int, [_I, _I, _I, _L, _P, _P, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
     "nfm_sym_invert_host": (c_int, [_I, _I, _I, _I, _L, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
     "nfm_sym_matvec_host": (c_int, [_I, _I, _L, _P, _P, _P, _I, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
+    "nfm_batch_inv_host": (c_int, [_I, _I, _I, _I, _L, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
+    "nfm_batch_det_host": (c_int, [_I, _I, _L, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
+    "nfm_batch_solve_host": (c_int, [_I, _I, _I, _I, _L, _P, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
 }
 
 _lib = None

@@ -18,6 +18,12 @@ int batch_inv_lu_impl(int n, const KParams& p, cudaStream_t s) {
   return DispatchN<InvBind<T, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s);
 }
 template int batch_inv_lu_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
+// NFM_ALGO_LU for n <= 3: pivoted Gauss-Jordan instead of the closed forms (n >= 4 is the same kernel as AUTO)
+template <typename T>
+int batch_inv_lu_small_impl(int n, const KParams& p, cudaStream_t s) {
+  return DispatchN<InvBind<T, NFM_ALGO_LU>::template Op, 1, 3>::run(n, p, s);
+}
+template int batch_inv_lu_small_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);
 #elif NFM_PART == 1
 template <typename T>
 int batch_inv_ldl_impl(int n, const KParams& p, cudaStream_t s) {

@@ -235,6 +235,8 @@ int nfm_batch_inv(int dtype, int n, int algo, int closed_form_reg, int64_t batch
   if (algo == NFM_ALGO_LDL)
     return finish(dtype == NFM_F32 ? batch_inv_ldl_impl<float>(n, a.p, s) : batch_inv_ldl_impl<double>(n, a.p, s));
   if (algo != NFM_ALGO_AUTO && algo != NFM_ALGO_LU) return fail(NFM_E_UNSUPPORTED, "batch_inv: algo must be AUTO, LU or LDL");
+  if (algo == NFM_ALGO_LU && n <= 3)  // pivoted elimination as documented, not the closed forms AUTO takes there
+    return finish(dtype == NFM_F32 ? batch_inv_lu_small_impl<float>(n, a.p, s) : batch_inv_lu_small_impl<double>(n, a.p, s));
   return finish(dtype == NFM_F32 ? batch_inv_lu_impl<float>(n, a.p, s) : batch_inv_lu_impl<double>(n, a.p, s));
 }
 

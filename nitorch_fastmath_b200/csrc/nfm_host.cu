@@ -130,4 +130,46 @@ int nfm_sym_matvec_host(int dtype, int n, int64_t batch, const void* h_mat, cons
                   });
 }
 
+int nfm_batch_inv_host(int dtype, int n, int algo, int closed_form_reg, int64_t batch, const void* h_a, void* h_out,
+                       void* d_workspace, size_t workspace_bytes, int64_t chunk, int nbuf, void** streams) {
+  if (n < 1 || n > NFM_MAX_N || h_a == nullptr) {
+    set_error("batch_inv_host: bad argument");
+    return NFM_E_BADARG;
+  }
+  const int nn = n * n;
+  const HostOperand ops[3] = {{h_a, nn}, {nullptr, 0}, {nullptr, 0}};
+  return pipeline(dtype, batch, ops, h_out, nn, d_workspace, workspace_bytes, chunk, nbuf, streams,
+                  [=](const void* const* d_in, void* d_out, i64 cnt, cudaStream_t s) {
+                    return nfm_batch_inv(dtype, n, algo, closed_form_reg, cnt, d_in[0], nn, d_out, nn, s);
+                  });
+}
+
+int nfm_batch_det_host(int dtype, int n, int64_t batch, const void* h_a, void* h_out, void* d_workspace,
+                       size_t workspace_bytes, int64_t chunk, int nbuf, void** streams) {
+  if (n < 1 || n > NFM_MAX_N || h_a == nullptr) {
+    set_error("batch_det_host: bad argument");
+    return NFM_E_BADARG;
+  }
+  const int nn = n * n;
+  const HostOperand ops[3] = {{h_a, nn}, {nullptr, 0}, {nullptr, 0}};
+  return pipeline(dtype, batch, ops, h_out, 1, d_workspace, workspace_bytes, chunk, nbuf, streams,
+                  [=](const void* const* d_in, void* d_out, i64 cnt, cudaStream_t s) {
+                    return nfm_batch_det(dtype, n, cnt, d_in[0], nn, d_out, 1, s);
+                  });
+}
+
+int nfm_batch_solve_host(int dtype, int n, int nrhs, int algo, int64_t batch, const void* h_a, const void* h_b, void* h_out,
+                         void* d_workspace, size_t workspace_bytes, int64_t chunk, int nbuf, void** streams) {
+  if (n < 1 || n > NFM_MAX_N || nrhs < 1 || h_a == nullptr || h_b == nullptr) {
+    set_error("batch_solve_host: bad argument");
+    return NFM_E_BADARG;
+  }
+  const int nn = n * n, nk = n * nrhs;
+  const HostOperand ops[3] = {{h_a, nn}, {h_b, nk}, {nullptr, 0}};
+  return pipeline(dtype, batch, ops, h_out, nk, d_workspace, workspace_bytes, chunk, nbuf, streams,
+                  [=](const void* const* d_in, void* d_out, i64 cnt, cudaStream_t s) {
+                    return nfm_batch_solve(dtype, n, nrhs, algo, cnt, d_in[0], nn, d_in[1], nk, d_out, nk, s);
+                  });
+}
+
 }  // extern "C"

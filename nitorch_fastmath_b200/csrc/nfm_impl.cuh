@@ -30,6 +30,7 @@ template <typename T> int sym_invert_part2(int n, int diag_only, const KParams& 
 // dense: part 0 = inverse (closed / Gauss-Jordan), part 1 = inverse (LDL^T) + det + matvec,
 // part 2 = solve LU, part 3 = solve LDL^T
 template <typename T> int batch_inv_lu_impl(int n, const KParams& p, cudaStream_t s);
+template <typename T> int batch_inv_lu_small_impl(int n, const KParams& p, cudaStream_t s);  // NFM_ALGO_LU, n <= 3
 template <typename T> int batch_inv_ldl_impl(int n, const KParams& p, cudaStream_t s);
 template <typename T> int batch_det_impl(int n, const KParams& p, cudaStream_t s);
 template <typename T> int batch_matvec_impl(int n, const KParams& p, cudaStream_t s);

@@ -920,7 +920,7 @@ int run_op(KParams p, cudaStream_t stream) {
     }
     }
     if (rc == 0) {
-      t_last_path_tma = 1;
+      t_last_path_tma = PoolTune<Op>::kEnabled ? 3 : 1;
       return NFM_OK;
     }
     if (rc > 0) {

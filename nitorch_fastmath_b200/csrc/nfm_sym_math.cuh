@@ -200,7 +200,11 @@ struct LDL {
 
   // Same factorisation, but reports whether every 1x1 pivot was acceptable:
   // |d_k| >= kPivotTol * max_i |a_ki| of the current Schur complement (the
-  // Bunch-Kaufman style test that bounds element growth) and finite.  SPD
+  // Bunch-Kaufman style test; with 0.1 a multiplier is at most 10, so growth is
+  // bounded but looser than partial pivoting -- a tighter tolerance would send
+  // legitimate SPD matrices with a wide diagonal range to the slow redo).
+  // Non-finite pivots are NOT caught (fmin drops NaN): such input yields
+  // non-finite output on either path, as in the reference.  SPD
   // matrices always pass; a symmetric indefinite matrix that fails is re-solved
   // with pivoted LU by the caller, which is what the reference does for every
   // matrix of order > 4 (_impl/sym.py:392-396).

@@ -27,6 +27,8 @@ def _devices(devices: Optional[Sequence[int]]) -> Sequence[int]:
         devices = list(range(torch.cuda.device_count()))
     if len(devices) == 0:
         raise ValueError("no devices given")
+    if len(set(devices)) != len(devices):
+        raise ValueError(f"duplicate device ids in {list(devices)}: each slab needs its own GPU")
     return devices
 
 

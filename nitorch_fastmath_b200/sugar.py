@@ -42,6 +42,20 @@ def lmdiv(a: Tensor, b: Tensor, method: str = 'lu', rcond: float = 1e-15, out: O
     dev = D.common_device(a, b)
     if dev.type != "cuda":
         cuda = _host.offload_device()
+        n, k = a.shape[-1], b.shape[-1]
+        plain = (a.dtype == b.dtype and a.dtype in D._DTYPE_CODE and a.is_contiguous() and b.is_contiguous()
+                 and 1 <= n <= _lib.MAX_N and b.shape[-2] == n and a.shape[:-2] == b.shape[:-2] and k > 0 and a.numel() > 0
+                 and (out is None or (out.device.type == "cpu" and out.is_contiguous() and out.dtype == a.dtype
+                                      and out.shape == b.shape)))
+        if plain:
+            # dense host batches are streamed through the GPU in chunks (nfm_batch_solve_host)
+            code = D.dtype_code(a.dtype)
+            nb = a.numel() // (n * n)
+            res = out if out is not None else torch.empty(b.shape, dtype=a.dtype, pin_memory=True)
+            _host.run_host("nfm_batch_solve_host", code, a.dtype, n * n + n * k, n * k, nb,
+                           lambda fn, ws, wsb, chunk, nbuf, streams: fn(code, n, k, algo, nb, a.data_ptr(), b.data_ptr(),
+                                                                         res.data_ptr(), ws, wsb, chunk, nbuf, streams))
+            return res
         r = lmdiv(a.to(cuda), b.to(cuda), method=method).cpu()
         if out is not None:
             out.copy_(r)
@@ -87,20 +101,12 @@ def inv(a: Tensor, method: str = 'lu', rcond: float = 1e-15, out: Optional[Tenso
     if a.shape[-1] != a.shape[-2]:
         raise NotImplementedError("non-square systems (pseudo-inverse) are outside the B200 hot path")
     algo = _algo(method)
-    r = batchinv(a, method='lu' if algo == _lib.ALGO_LU else 'chol', regularise=False)
-    if out is not None:
-        out.copy_(r)
-        return out
-    return r
+    return batchinv(a, method='lu' if algo == _lib.ALGO_LU else 'chol', regularise=False, out=out)
 
 
 def matvec(mat: Tensor, vec: Tensor, out: Optional[Tensor] = None) -> Tensor:
     r"""Matrix-vector product with broadcasting (reference sugar.py:261-287)."""
-    r = batchmatvec(mat, vec)
-    if out is not None:
-        out.copy_(r)
-        return out
-    return r
+    return batchmatvec(mat, vec, out=out)
 
 
 def solvevec(mat: Tensor, vec: Tensor, method: str = 'lu', rcond: float = 1e-15,

@@ -203,7 +203,10 @@ def _as_diag(diag, n: int, dtype: torch.dtype, device: torch.device) -> Optional
     if diag is None:
         return None
     if torch.is_tensor(diag) and diag.dim() >= 1 and diag.shape[-1] in (1, n):
-        return diag.to(device=device, dtype=dtype).expand(*diag.shape[:-1], n)
+        r = diag.to(device=device, dtype=dtype).expand(*diag.shape[:-1], n)
+        # a 1-D regulariser is handed to the library as ONE dense record of n values: a
+        # shape-(1,) tensor (stride 0 after expand) or a strided slice must be materialised
+        return r if r.dim() > 1 or r.is_contiguous() else r.contiguous()
     key = None
     if isinstance(diag, (int, float)):
         key = ((float(diag),), n, dtype, device)
@@ -541,8 +544,11 @@ def sym_matmul(j: Tensor, h: Tensor) -> Tensor:
     k, d = j.shape[-2:]
     if not (1 <= k <= _lib.MAX_N and 1 <= d <= _lib.MAX_N):
         raise ValueError(f"sym_matmul supports 1 <= k, d <= {_lib.MAX_N}")
+    if h.shape[-1] == k and k > 1:
+        # diagonal Hessian (reference jhjn accepts it: _impl/sym.py:603-606): packed form with zero off-diagonals
+        h = torch.cat([h, h.new_zeros((*h.shape[:-1], k * (k - 1) // 2))], -1)
     if h.shape[-1] != k * (k + 1) // 2:
-        raise ValueError("only compact symmetric h (k*(k+1)//2 coefficients) is supported")
+        raise ValueError("h must be compact symmetric (k*(k+1)//2 coefficients) or diagonal (k coefficients)")
     cdt = h.dtype if h.dtype in (torch.float32, torch.float64) else D.compute_dtype(j, h)
     mode = 1 if (k == d and k <= 3) else 0
     batch = tuple(torch.broadcast_shapes(j.shape[:-2], h.shape[:-1]))

@@ -1,8 +1,11 @@
-"""Import the *real* reference from /root/reference (build container only).
+"""Import the *real*, unmodified reference: from /root/reference in the build
+container, else from the git-ignored install ``baseline/_ref/`` that
+``oracle/install_reference.py`` makes (it travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY -- used by ``oracle/validate_against_reference.py``
-and ``tests/golden/make_golden.py``.  /root/reference does not exist on the
-GPU box; nothing that runs there may call this.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY -- used by
+``oracle/validate_against_reference.py``, ``tests/golden/make_golden.py`` and
+the reference arm of ``bench.py`` (``--impl reference``).  Nothing under
+nitorch_fastmath_b200/ imports it.
 
 ``import nitorch_fastmath`` needs the un-vendored ``jitfields`` package
 (sym.py:37, tests/utils.py:2).  Following SURVEY.md appendix A.6 we load
@@ -19,7 +22,18 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("NFM_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    env = os.environ.get("NFM_REFERENCE_ROOT")
+    for root in ([env] if env else []) + ["/root/reference", os.path.join(_REPO, "baseline", "_ref")]:
+        if os.path.isfile(os.path.join(root, "nitorch_fastmath", "_impl", "sym.py")):
+            return root
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

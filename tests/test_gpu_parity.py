@@ -228,7 +228,7 @@ def test_pool_kernel_tile_boundaries(nfm, batch):
         a = _row_permuted(G.dense_shifted(batch, n, dtype, seed=batch + n), seed=batch)
         b = G.vectors(batch, n, dtype, seed=batch + 1)
         x = nfm.batchinv(a.to(DEV))
-        assert _lib.load().nfm_last_path_was_tma() == 1
+        assert _lib.load().nfm_last_path_was_tma() == 3      # TMA-staged warp-pool kernel
         close(x, P.batchinv(a), dtype, 2, scale=4)
         close(nfm.batchdet(a.to(DEV)), P.batchdet(a), dtype, 0, scale=4)
         close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), dtype, scale=4)
@@ -656,6 +656,30 @@ def test_host_pipeline(nfm, n):
     assert torch.equal(y, nfm.sym_matvec(mat.to(DEV), vec.to(DEV)).cpu())
     # non-plain host operands take the whole-upload path
     close(nfm.sym_solve(mat[:1000, :], vec[0]), P.sym_solve(mat[:1000], vec[0]), dtype)
+
+
+@pytest.mark.parametrize("n,dtype", [(4, torch.float64), (3, torch.float32), (8, torch.float64)])
+def test_host_pipeline_dense(nfm, n, dtype):
+    """CPU operands of the dense routines are streamed through the GPU in chunks
+    (nfm_batch_*_host): same bits as the device call, results on the CPU."""
+    batch = 300_007
+    a = G.dense_shifted(batch, n, dtype, seed=n).pin_memory()
+    b = G.vectors(batch, n, dtype, seed=n + 1).pin_memory()
+    b3 = G.vectors((batch, n), 3, dtype, seed=n + 2).pin_memory()
+    da, db, db3 = a.to(DEV), b.to(DEV), b3.to(DEV)
+    inv = nfm.batchinv(a)
+    assert inv.device.type == "cpu" and torch.equal(inv, nfm.batchinv(da).cpu())
+    assert torch.equal(nfm.batchdet(a), nfm.batchdet(da).cpu())
+    x = nfm.solvevec(a, b)
+    assert x.device.type == "cpu" and torch.equal(x, nfm.solvevec(da, db).cpu())
+    assert torch.equal(nfm.lmdiv(a, b3), nfm.lmdiv(da, db3).cpu())
+    out = torch.empty_like(b).pin_memory()
+    assert nfm.solvevec(a, b, out=out) is out and torch.equal(out, x)
+    sl = slice(150_000, 152_000)
+    close(x[sl], P.solvevec(a[sl], b[sl]), dtype)
+    close(inv[sl], P.batchinv(a[sl]), dtype, 2)
+    # non-plain host operands (a strided view) take the whole-upload path
+    close(nfm.batchinv(a[::7]), P.batchinv(a[::7]), dtype, 2)
 
 
 def test_single_process_multi_gpu_host_sharding(nfm):
