@@ -348,6 +348,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--workloads", default=None,
+                    help="comma-separated list: several workloads in one process, one JSON line each (saves start-up on multi-GPU boxes)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -357,6 +359,25 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world != 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dist = None
+    if args.impl == "ours" and world > 1:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU path in the product)")
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    names = args.workloads.split(",") if args.workloads else [args.workload]
+    for name in names:
+        if name not in WORKLOADS:
+            raise SystemExit(f"unknown workload {name}")
+        args.workload = name
+        run_workload(args, rank, local_rank, world, dist)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_workload(args, rank, local_rank, world, dist):
 
     w = dict(WORKLOADS[args.workload])
     if args.kind or args.n or args.dtype:
@@ -398,11 +419,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1 and os.environ.get("NFM_BENCH_BIND") == "1":   # optional: measured no gain on this pool's hosts
         timing["cpu_affinity"] = bind_to_gpu_cpus(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
     begin, end = shard_bounds(batch, world, rank)
     my = end - begin
     code = 0 if dtype == torch.float32 else 1
@@ -512,10 +528,9 @@ def main():
                 "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e}
         if base is not None:
             line["cpu_baseline"] = base
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    del sets, launchers
+    torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

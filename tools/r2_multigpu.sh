@@ -19,9 +19,7 @@ done
 for n in 1 2 4 8; do
   [ $n -le $NG ] || continue
   run $n --workload sym_solve3 --steps 200 --warmup 20 --no-cpu 2>/dev/null | grep '^{' >> $OUT.jsonl
-  for w in sym_solve6 sym_invert6 sym_solve10; do
-    run $n --workload $w --steps 100 --warmup 10 --no-cpu --no-e2e 2>/dev/null | grep '^{' >> $OUT.jsonl
-  done
+  run $n --workloads sym_solve6,sym_invert6,sym_solve10,sym_solve3_1m --steps 100 --warmup 10 --no-cpu --no-e2e 2>/dev/null | grep '^{' >> $OUT.jsonl
 done
 # the driver's own protocol (20 steps) for config 2 at the largest N, and chunk-size sensitivity of the e2e path
 run $NG --workload sym_solve3 --steps 20 --warmup 3 --no-cpu --no-e2e 2>/dev/null | grep '^{' >> $OUT.jsonl
