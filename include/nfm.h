@@ -184,12 +184,26 @@ int nfm_sym_outer(int dtype, int n, int64_t batch,
  * and what its general branch jhjn computes (:596-634).
  * mode 1: out = J H J^T  (k == d) -- what the reference's unrolled branches
  * jhj1/2/3 compute for k == d <= 3 (:532-593).  1 <= k, d <= 10 (register
- * kernels up to 4 x 4, a run-time-sized kernel above).
+ * kernels up to 6 x 6, a run-time-sized kernel above).
  * Replaces sym_matmul _impl/sym.py:637-670. */
 int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch,
                    const void *jac, int64_t jac_stride,
                    const void *hess, int64_t hess_stride,
                    void *out, int64_t out_stride, void *stream);
+
+/* Fused Gauss-Newton system: the packed Hessian
+ * J^T H J is built in registers and solved at once, it never goes to HBM:
+ *     out = (J^T H J + diag(d))^-1 g          (mode 0)
+ *     out = (J H J^T + diag(d))^-1 g          (mode 1, k == d <= 3: the reference's unrolled branches)
+ * jac: k x d row-major, hess: packed k(k+1)/2 (mode 0), grad / diag / out: records of d
+ * (mode 0); diag may be NULL.  1 <= k, d <= 6.
+ * Replaces the chain sym_matmul -> sym_solve, _impl/sym.py:637-670 then :327-398. */
+int nfm_sym_matmul_solve(int dtype, int k, int d, int mode, int64_t batch,
+                         const void *jac, int64_t jac_stride,
+                         const void *hess, int64_t hess_stride,
+                         const void *grad, int64_t grad_stride,
+                         const void *diag, int64_t diag_stride,
+                         void *out, int64_t out_stride, void *stream);
 
 /* Fused regularised solve + update (the chain
  * sym_solve_ -> sym_submatvec_/sub_ of a Gauss-Newton / Levenberg-Marquardt
@@ -203,6 +217,17 @@ int nfm_sym_solve_update(int dtype, int n, int algo, int64_t batch,
                          const void *x, int64_t x_stride,
                          double lam, double alpha,
                          void *out, int64_t out_stride, void *stream);
+
+/* The same with a per-matrix diagonal regulariser (the documented regulariser of
+ * the reference, _impl/sym.py:356-357) as a fourth staged operand:
+ *     out = x - alpha * (A + lam I + diag(d))^-1 v ;   diag: records of n, may be NULL. */
+int nfm_sym_solve_update_reg(int dtype, int n, int algo, int64_t batch,
+                             const void *mat, int64_t mat_stride,
+                             const void *vec, int64_t vec_stride,
+                             const void *x, int64_t x_stride,
+                             const void *diag, int64_t diag_stride,
+                             double lam, double alpha,
+                             void *out, int64_t out_stride, void *stream);
 
 /* ---- host-buffer pipelines (end-to-end path) --------------------------- */
 

@@ -147,6 +147,44 @@ def out_operand(out: Optional[torch.Tensor], shape: Tuple[int, ...], rec_ndim: i
     return Operand(out, stride, estride), out, False
 
 
+def outer_split(batch_shape: Tuple[int, ...], operands: Sequence[Tuple[Optional[torch.Tensor], int]],
+                max_outer: int = 512) -> int:
+    """Partially broadcast operands (e.g. one Hessian field ``(1, X, Y, Z, NN)`` for a batch of
+    gradient fields ``(B, X, Y, Z, N)``) do not collapse to one batch stride.  Instead of
+    materialising them, the leading ``s`` batch dims can be looped over: returns the smallest
+    ``s > 0`` such that every operand, expanded to ``batch_shape``, collapses over dims ``[s:]``
+    -- or 0 when no split is needed, none exists, or it would take more than ``max_outer`` launches."""
+    nb = len(batch_shape)
+
+    def collapses(s: int) -> bool:
+        for t, rec_ndim in operands:
+            if t is None:
+                continue
+            rec_shape = tuple(t.shape[t.dim() - rec_ndim:]) if rec_ndim else ()
+            full = t.expand(*batch_shape, *rec_shape)
+            c = _collapse(full.shape[s:nb], full.stride()[s:nb])
+            if c is not None and c < 0:
+                return False
+        return True
+
+    if nb < 2 or collapses(0):
+        return 0
+    for s in range(1, nb):
+        if math.prod(batch_shape[:s]) > max_outer:
+            return 0
+        if collapses(s):
+            return s
+    return 0
+
+
+def outer_views(t: Optional[torch.Tensor], batch_shape: Tuple[int, ...], rec_ndim: int, idx: Tuple[int, ...]):
+    """The slice ``idx`` (over the leading batch dims) of ``t`` expanded to ``batch_shape``: a view."""
+    if t is None:
+        return None
+    rec_shape = tuple(t.shape[t.dim() - rec_ndim:]) if rec_ndim else ()
+    return t.expand(*batch_shape, *rec_shape)[idx]
+
+
 def batch_count(batch_shape: Sequence[int]) -> int:
     return math.prod(batch_shape)
 
@@ -194,6 +232,20 @@ def plain_cuda(ref: torch.Tensor, *others: Optional[torch.Tensor]) -> bool:
         if t.device != ref.device or t.dtype != ref.dtype or not t.is_contiguous() or t.shape[:-1] != lead:
             return False
     return True
+
+
+def empty_like_phased(ref: torch.Tensor, shape=None) -> torch.Tensor:
+    """``torch.empty`` with ``ref``'s dtype / device whose address has the same offset from a
+    16-byte boundary as ``ref``'s.  A dense view that starts inside its storage (``field[1:]``)
+    is not 16-byte aligned; the library can still put it on the TMA path by peeling off a few
+    leading matrices -- but only if the output, which has records of the same length, is out of
+    phase by the same amount."""
+    shape = tuple(ref.shape) if shape is None else tuple(shape)
+    off = (ref.data_ptr() % 16) // ref.element_size()
+    if off == 0:
+        return torch.empty(shape, dtype=ref.dtype, device=ref.device)
+    buf = torch.empty(math.prod(shape) + off, dtype=ref.dtype, device=ref.device)
+    return buf[off:].view(shape)
 
 
 class device_of:

@@ -49,6 +49,8 @@ SIGNATURES = {
     "nfm_sym_outer": (c_int, [_I, _I, _L, _P, _L, _P, _L, _P]),
     "nfm_sym_matmul": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P]),
     "nfm_sym_solve_update": (c_int, [_I, _I, _I, _L, _P, _L, _P, _L, _P, _L, ctypes.c_double, ctypes.c_double, _P, _L, _P]),
+    "nfm_sym_matmul_solve": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P]),
+    "nfm_sym_solve_update_reg": (c_int, [_I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P, _L, ctypes.c_double, ctypes.c_double, _P, _L, _P]),
     "nfm_host_workspace_bytes": (c_size_t, [_I, _L, _I, _I, _I]),
     "nfm_sym_solve_host": (c_int, [_I, _I, _I, _L, _P, _P, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),
     "nfm_sym_invert_host": (c_int, [_I, _I, _I, _I, _L, _P, _P, _P, c_size_t, _L, _I, ctypes.POINTER(c_void_p)]),

@@ -25,7 +25,7 @@ struct Operand {
 
 __host__ __device__ inline i64 elem_stride(i64 estride) { return estride == 0 ? 1 : estride; }
 
-constexpr int kMaxIn = 3;
+constexpr int kMaxIn = 4;
 
 // Launch parameter block shared by every op.
 struct KParams {

@@ -57,75 +57,6 @@ struct SymOuterOp {
   }
 };
 
-// J^T H J (mode 0) or J H J^T (mode 1, K == D), packed output (_impl/sym.py:532-670)
-template <typename T, int K, int D, int MODE>
-struct SymMatmulOp {
-  using scalar = T;
-  static constexpr int kHN = MODE == 0 ? K : D;   // order of H
-  static constexpr int kON = MODE == 0 ? D : K;   // order of the result
-  static constexpr int kLen0 = K * D, kLen1 = packed_len(kHN), kLen2 = 1, kUse = 3, kOut = packed_len(kON);
-  static constexpr bool kHeavy = false;
-  __device__ static __forceinline__ void apply(const T (&j)[kLen0], const T (&h)[kLen1], const T (&)[1], int, int, T (&out)[kOut]) {
-    // G = J as (kON x kHN) "rows = output index": mode 0 uses J^T, mode 1 uses J
-    T hj[kHN][kON];  // H * G^T
-#pragma unroll
-    for (int a = 0; a < kHN; ++a)
-#pragma unroll
-      for (int o = 0; o < kON; ++o) {
-        T s = T(0);
-#pragma unroll
-        for (int b = 0; b < kHN; ++b) {
-          const T g = MODE == 0 ? j[b * D + o] : j[o * D + b];
-          s += h[pidx(kHN, a, b)] * g;
-        }
-        hj[a][o] = s;
-      }
-#pragma unroll
-    for (int o = 0; o < kON; ++o)
-#pragma unroll
-      for (int q = o; q < kON; ++q) {
-        T s = T(0);
-#pragma unroll
-        for (int a = 0; a < kHN; ++a) {
-          const T g = MODE == 0 ? j[a * D + o] : j[o * D + a];
-          s += g * hj[a][q];
-        }
-        out[pidx(kON, o, q)] = s;
-      }
-  }
-};
-
-template <typename T, int K, int D>
-static int matmul_run(int mode, const KParams& p, cudaStream_t s) {
-  if (mode == 0) return run_op<SymMatmulOp<T, K, D, 0>>(p, s);
-  if constexpr (K == D) return run_op<SymMatmulOp<T, K, D, 1>>(p, s);
-  else return NFM_E_UNSUPPORTED;
-}
-
-template <typename T, int K>
-static int matmul_d(int d, int mode, const KParams& p, cudaStream_t s) {
-  switch (d) {
-    case 1: return matmul_run<T, K, 1>(mode, p, s);
-    case 2: return matmul_run<T, K, 2>(mode, p, s);
-    case 3: return matmul_run<T, K, 3>(mode, p, s);
-    case 4: return matmul_run<T, K, 4>(mode, p, s);
-  }
-  return NFM_E_UNSUPPORTED;
-}
-
-template <typename T>
-static int matmul_kd(int k, int d, int mode, const KParams& p, cudaStream_t s) {
-  switch (k) {
-    case 1: return matmul_d<T, 1>(d, mode, p, s);
-    case 2: return matmul_d<T, 2>(d, mode, p, s);
-    case 3: return matmul_d<T, 3>(d, mode, p, s);
-    case 4: return matmul_d<T, 4>(d, mode, p, s);
-  }
-  return NFM_E_UNSUPPORTED;
-}
-
-template <typename T, int ALGO> struct SolveUpdBind { template <int N> using Op = SymSolveUpdateOp<T, N, ALGO>; };
-
 template <typename T> struct SDetBind { template <int N> using Op = SymDetOp<T, N>; };
 template <typename T> struct SFullBind { template <int N> using Op = SymToFullOp<T, N>; };
 template <typename T> struct SOuterBind { template <int N> using Op = SymOuterOp<T, N>; };
@@ -171,8 +102,8 @@ int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch, const void*
     return NFM_E_UNSUPPORTED;
   }
   if (batch < 0 || !jac || !hess || !out || jac_stride < 0 || hess_stride < 0 || out_stride < 0) { set_error("bad argument"); return NFM_E_BADARG; }
-  if (k > 4 || d > 4) {  // run-time-sized kernel above the templated 4 x 4
-    auto st = static_cast<cudaStream_t>(stream);
+  auto st = static_cast<cudaStream_t>(stream);
+  if (k > kFusedMaxOrder || d > kFusedMaxOrder || (mode == 1 && k > 3)) {  // run-time-sized kernel above the templated 6 x 6
     const int rc = dtype == NFM_F32 ? sym_matmul_rt<float>(k, d, mode, batch, jac, jac_stride, hess, hess_stride, out, out_stride, st)
                                     : sym_matmul_rt<double>(k, d, mode, batch, jac, jac_stride, hess, hess_stride, out, out_stride, st);
     if (rc) set_error("sym_matmul kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
@@ -187,17 +118,49 @@ int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch, const void*
   p.out = out;
   p.out_stride = out_stride;
   p.batch = batch;
-  auto s = static_cast<cudaStream_t>(stream);
-  return dtype == NFM_F32 ? matmul_kd<float>(k, d, mode, p, s) : matmul_kd<double>(k, d, mode, p, s);
+  return dtype == NFM_F32 ? sym_matmul_impl<float>(k, d, mode, p, st) : sym_matmul_impl<double>(k, d, mode, p, st);
 }
 
-int nfm_sym_solve_update(int dtype, int n, int algo, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,
-                         int64_t vec_stride, const void* x, int64_t x_stride, double lam, double alpha, void* out,
-                         int64_t out_stride, void* stream) {
+int nfm_sym_matmul_solve(int dtype, int k, int d, int mode, int64_t batch, const void* jac, int64_t jac_stride, const void* hess,
+                         int64_t hess_stride, const void* grad, int64_t grad_stride, const void* diag, int64_t diag_stride,
+                         void* out, int64_t out_stride, void* stream) {
+  if (dtype != NFM_F32 && dtype != NFM_F64) { set_error("dtype must be NFM_F32 or NFM_F64"); return NFM_E_UNSUPPORTED; }
+  if (k < 1 || k > kFusedMaxOrder || d < 1 || d > kFusedMaxOrder || (mode != 0 && mode != 1) || (mode == 1 && (k != d || k > 3))) {
+    set_error("sym_matmul_solve: 1 <= k, d <= 6; mode 1 needs k == d <= 3");
+    return NFM_E_UNSUPPORTED;
+  }
+  if (batch < 0 || !jac || !hess || !grad || !out || jac_stride < 0 || hess_stride < 0 || grad_stride < 0 || diag_stride < 0 ||
+      out_stride < 0) {
+    set_error("bad argument");
+    return NFM_E_BADARG;
+  }
+  KParams p{};
+  p.in[0].ptr = jac;
+  p.in[0].stride = jac_stride;
+  p.in[1].ptr = hess;
+  p.in[1].stride = hess_stride;
+  p.in[2].ptr = grad;
+  p.in[2].stride = grad_stride;
+  p.present = 7;
+  if (diag != nullptr) {
+    p.in[3].ptr = diag;
+    p.in[3].stride = diag_stride;
+    p.present |= 8;
+  }
+  p.out = out;
+  p.out_stride = out_stride;
+  p.batch = batch;
+  auto st = static_cast<cudaStream_t>(stream);
+  return dtype == NFM_F32 ? sym_matmul_solve_impl<float>(k, d, mode, p, st) : sym_matmul_solve_impl<double>(k, d, mode, p, st);
+}
+
+int nfm_sym_solve_update_reg(int dtype, int n, int algo, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,
+                             int64_t vec_stride, const void* x, int64_t x_stride, const void* diag, int64_t diag_stride, double lam,
+                             double alpha, void* out, int64_t out_stride, void* stream) {
   if (dtype != NFM_F32 && dtype != NFM_F64) { set_error("dtype must be NFM_F32 or NFM_F64"); return NFM_E_UNSUPPORTED; }
   if (n < 1 || n > NFM_MAX_N) { set_error("matrix order must be in 1..10"); return NFM_E_UNSUPPORTED; }
   if (algo != NFM_ALGO_AUTO && algo != NFM_ALGO_LDL) { set_error("sym_solve_update: algo must be AUTO or LDL"); return NFM_E_UNSUPPORTED; }
-  if (batch < 0 || !mat || !vec || !x || !out || mat_stride < 0 || vec_stride < 0 || x_stride < 0 || out_stride < 0) {
+  if (batch < 0 || !mat || !vec || !x || !out || mat_stride < 0 || vec_stride < 0 || x_stride < 0 || diag_stride < 0 || out_stride < 0) {
     set_error("bad argument");
     return NFM_E_BADARG;
   }
@@ -209,18 +172,25 @@ int nfm_sym_solve_update(int dtype, int n, int algo, int64_t batch, const void* 
   p.in[2].ptr = x;
   p.in[2].stride = x_stride;
   p.present = 7;
+  if (diag != nullptr) {
+    p.in[3].ptr = diag;
+    p.in[3].stride = diag_stride;
+    p.present |= 8;
+  }
   p.out = out;
   p.out_stride = out_stride;
   p.batch = batch;
   p.scal0 = lam;
   p.scal1 = alpha;
   auto s = static_cast<cudaStream_t>(stream);
-  if (algo == NFM_ALGO_LDL) {
-    return dtype == NFM_F32 ? DispatchN<SolveUpdBind<float, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s)
-                            : DispatchN<SolveUpdBind<double, NFM_ALGO_LDL>::template Op, 1, NFM_MAX_N>::run(n, p, s);
-  }
-  return dtype == NFM_F32 ? DispatchN<SolveUpdBind<float, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s)
-                          : DispatchN<SolveUpdBind<double, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s);
+  return dtype == NFM_F32 ? sym_solve_update_impl<float>(n, algo, p, s) : sym_solve_update_impl<double>(n, algo, p, s);
+}
+
+int nfm_sym_solve_update(int dtype, int n, int algo, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,
+                         int64_t vec_stride, const void* x, int64_t x_stride, double lam, double alpha, void* out,
+                         int64_t out_stride, void* stream) {
+  return nfm_sym_solve_update_reg(dtype, n, algo, batch, mat, mat_stride, vec, vec_stride, x, x_stride, nullptr, 0, lam, alpha, out,
+                                  out_stride, stream);
 }
 
 }  // extern "C"

@@ -48,6 +48,12 @@ template <typename T>
 int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out, i64 os,
                    cudaStream_t s);
 
+// nfm_fused.cu: register kernels for 1 <= k, d <= 6 (kFusedMaxOrder)
+constexpr int kFusedMaxOrder = 6;
+template <typename T> int sym_matmul_impl(int k, int d, int mode, const KParams& p, cudaStream_t s);
+template <typename T> int sym_matmul_solve_impl(int k, int d, int mode, const KParams& p, cudaStream_t s);
+template <typename T> int sym_solve_update_impl(int n, int algo, const KParams& p, cudaStream_t s);
+
 template <typename T>
 int sym_matmul_rt(int k, int d, int mode, i64 batch, const void* jac, i64 js, const void* hess, i64 hs, void* out, i64 os,
                   cudaStream_t s);

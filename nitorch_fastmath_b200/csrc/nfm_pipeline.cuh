@@ -31,6 +31,7 @@
 // An Op is a stateless struct:
 //     using scalar = float|double;
 //     static constexpr int kLen0, kLen1, kLen2;   // input record lengths (1 if unused)
+//     [static constexpr int kLen3;]               // optional fourth input (bit 8 of kUse)
 //     static constexpr int kUse;                   // bit mask of inputs the op can take
 //     static constexpr int kOut;                   // output record length
 //     static constexpr bool kHeavy;                // pivoted / long dependent chains (tile geometry hint)
@@ -55,11 +56,23 @@ struct has_scalars : std::false_type {};
 template <class Op>
 struct has_scalars<Op, std::void_t<decltype(Op::kScalars)>> : std::true_type {};
 
-template <class Op, class R0, class R1, class R2, class O>
-__device__ __forceinline__ void apply_op(const KParams& p, const R0& r0, const R1& r1, const R2& r2, O& o) {
+// Ops with a FOURTH input operand declare `kLen3` (bit 8 of kUse) and take it as an
+// extra record argument of apply(); everyone else sees a dummy of length 1.
+template <class Op, class = void>
+struct len3 { static constexpr int value = 1; static constexpr bool has = false; };
+template <class Op>
+struct len3<Op, std::void_t<decltype(Op::kLen3)>> { static constexpr int value = Op::kLen3; static constexpr bool has = true; };
+
+template <class Op, class R0, class R1, class R2, class R3, class O>
+__device__ __forceinline__ void apply_op(const KParams& p, const R0& r0, const R1& r1, const R2& r2, const R3& r3, O& o) {
   using T = typename Op::scalar;
-  if constexpr (has_scalars<Op>::value) Op::apply(r0, r1, r2, p.present, p.flags, T(p.scal0), T(p.scal1), o);
-  else Op::apply(r0, r1, r2, p.present, p.flags, o);
+  if constexpr (len3<Op>::has) {
+    if constexpr (has_scalars<Op>::value) Op::apply(r0, r1, r2, r3, p.present, p.flags, T(p.scal0), T(p.scal1), o);
+    else Op::apply(r0, r1, r2, r3, p.present, p.flags, o);
+  } else {
+    if constexpr (has_scalars<Op>::value) Op::apply(r0, r1, r2, p.present, p.flags, T(p.scal0), T(p.scal1), o);
+    else Op::apply(r0, r1, r2, p.present, p.flags, o);
+  }
 }
 
 constexpr int kSegs = 8;     // segments per tile in the SEG layout
@@ -82,6 +95,7 @@ struct TileGeom {
   static constexpr int bytes(int len) { return kTile * len * int(sizeof(T)); }
   static constexpr int footprint(int len) { return bytes(len) + kPad; }
   static constexpr int kBytes0 = bytes(Op::kLen0), kBytes1 = bytes(Op::kLen1), kBytes2 = bytes(Op::kLen2);
+  static constexpr int kBytes3 = bytes(len3<Op>::value);
   static constexpr int kBytesOut = bytes(Op::kOut);
   static constexpr int kFootOut = footprint(Op::kOut);
   static_assert(kTile % kTileGran == 0, "tile capacity must be a multiple of kTileGran matrices");
@@ -212,8 +226,11 @@ __global__ void __launch_bounds__(THREADS)
   const int f0 = (staged & 1) ? G::footprint(Op::kLen0) : 0;
   const int f1 = (staged & 2) ? G::footprint(Op::kLen1) : 0;
   const int f2 = (staged & 4) ? G::footprint(Op::kLen2) : 0;
-  const int stage_bytes = f0 + f1 + f2;
-  const int staged_len = ((staged & 1) ? Op::kLen0 : 0) + ((staged & 2) ? Op::kLen1 : 0) + ((staged & 4) ? Op::kLen2 : 0);
+  constexpr int kL3 = len3<Op>::value;
+  const int f3 = (staged & 8) ? G::footprint(kL3) : 0;
+  const int stage_bytes = f0 + f1 + f2 + f3;
+  const int staged_len = ((staged & 1) ? Op::kLen0 : 0) + ((staged & 2) ? Op::kLen1 : 0) + ((staged & 4) ? Op::kLen2 : 0) +
+                         ((staged & 8) ? kL3 : 0);
 
   unsigned char* const in_base = smem;
   unsigned char* const out_base = smem + STAGES * stage_bytes;
@@ -223,6 +240,7 @@ __global__ void __launch_bounds__(THREADS)
   const T* const g0 = static_cast<const T*>(p.in[0].ptr);
   const T* const g1 = static_cast<const T*>(p.in[1].ptr);
   const T* const g2 = static_cast<const T*>(p.in[2].ptr);
+  const T* const g3 = static_cast<const T*>(p.in[3].ptr);
   T* const gout = static_cast<T*>(p.out);
   // matrices in tile t
   auto count_of = [&](i64 t) { return t < ntiles ? tile_m : part_m; };
@@ -248,6 +266,7 @@ __global__ void __launch_bounds__(THREADS)
       if (staged & 1) bulk_prefetch_l2(g0 + first * Op::kLen0, c * Op::kLen0 * es);
       if (staged & 2) bulk_prefetch_l2(g1 + first * Op::kLen1, c * Op::kLen1 * es);
       if (staged & 4) bulk_prefetch_l2(g2 + first * Op::kLen2, c * Op::kLen2 * es);
+      if (staged & 8) bulk_prefetch_l2(g3 + first * kL3, c * kL3 * es);
     }
   }
 #endif
@@ -281,6 +300,13 @@ __global__ void __launch_bounds__(THREADS)
       bulk_g2s<kHint>(dst + f0 + f1 + seg * G::seg_stride(Op::kLen2),
                       reinterpret_cast<const unsigned char*>(g2 + first * Op::kLen2) + seg * sb, sb, &full[stage], policy);
     }
+    if constexpr (len3<Op>::has) {
+      if (staged & 8) {
+        const int sb = per_seg * kL3 * es;
+        bulk_g2s<kHint>(dst + f0 + f1 + f2 + seg * G::seg_stride(kL3), reinterpret_cast<const unsigned char*>(g3 + first * kL3) + seg * sb,
+                        sb, &full[stage], policy);
+      }
+    }
   };
 
   if (tid < kIssuers) {
@@ -308,10 +334,17 @@ __global__ void __launch_bounds__(THREADS)
     // are one record for the whole batch, re-read through L1; absent ones are 0.
     // Thread slots at or beyond cnt (a tile cut below capacity) compute on
     // whatever the buffer holds and their results are never stored.
-    T r0[MPT][Op::kLen0], r1[MPT][Op::kLen1], r2[MPT][Op::kLen2];
+    T r0[MPT][Op::kLen0], r1[MPT][Op::kLen1], r2[MPT][Op::kLen2], r3[MPT][kL3];
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       const int m = tid + j * THREADS;
+      if constexpr (len3<Op>::has) {
+        if (staged & 8) load_record(reinterpret_cast<const T*>(sin + f0 + f1 + f2 + G::template rec_offset<kL3>(m)), r3[j]);
+        else if (p.present & 8) load_record_scalar(g3, r3[j]);
+        else zero_record(r3[j]);
+      } else {
+        zero_record(r3[j]);
+      }
       if (staged & 1) load_record(reinterpret_cast<const T*>(sin + G::template rec_offset<Op::kLen0>(m)), r0[j]);
       else if (p.present & 1) load_record_scalar(g0, r0[j]);
       else zero_record(r0[j]);
@@ -335,7 +368,7 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
       T o[Op::kOut];
-      apply_op<Op>(p, r0[j], r1[j], r2[j], o);
+      apply_op<Op>(p, r0[j], r1[j], r2[j], r3[j], o);
       store_record(reinterpret_cast<T*>(sout + G::template rec_offset<Op::kOut>(tid + j * THREADS)), o);
     }
     fence_proxy_async();
@@ -523,8 +556,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
 
 #pragma unroll
     for (int j = 0; j < MPT; ++j) {
-      T o[Op::kOut];
-      apply_op<Op>(p, r0[j], r1[j], r2[j], o);
+      T o[Op::kOut], r3[len3<Op>::value];
+      zero_record(r3);  // pool ops take at most three inputs
+      apply_op<Op>(p, r0[j], r1[j], r2[j], r3, o);
       store_record(reinterpret_cast<T*>(sbuf + G::template rec_offset<Op::kOut>(lane + j * 32)), o);
     }
     if (ragged) {
@@ -566,14 +600,17 @@ __global__ void __launch_bounds__(128) strided_kernel(const __grid_constant__ KP
   for (i64 b0 = i64(blockIdx.x) * blockDim.x; b0 < p.batch; b0 += i64(gridDim.x) * blockDim.x) {
     const bool valid = b0 + threadIdx.x < p.batch;
     const i64 b = valid ? b0 + threadIdx.x : p.batch - 1;
-    T r0[Op::kLen0], r1[Op::kLen1], r2[Op::kLen2], o[Op::kOut];
+    T r0[Op::kLen0], r1[Op::kLen1], r2[Op::kLen2], r3[len3<Op>::value], o[Op::kOut];
     zero_record(r0);
     zero_record(r1);
     zero_record(r2);
+    zero_record(r3);
     if (p.present & 1) load_record_scalar(g0 + b * p.in[0].stride, r0, elem_stride(p.in[0].estride));
     if (p.present & 2) load_record_scalar(g1 + b * p.in[1].stride, r1, elem_stride(p.in[1].estride));
     if (p.present & 4) load_record_scalar(g2 + b * p.in[2].stride, r2, elem_stride(p.in[2].estride));
-    apply_op<Op>(p, r0, r1, r2, o);
+    if constexpr (len3<Op>::has)
+      if (p.present & 8) load_record_scalar(static_cast<const T*>(p.in[3].ptr) + b * p.in[3].stride, r3, elem_stride(p.in[3].estride));
+    apply_op<Op>(p, r0, r1, r2, r3, o);
     if (valid) store_record_scalar(gout + b * p.out_stride, o, elem_stride(p.out_estride));
   }
 }
@@ -600,11 +637,18 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // 227 KB limit.  TuneFixed pins ops whose measured optimum differs.
 // -DNFM_TUNE_TILE / NFM_TUNE_THREADS / NFM_TUNE_STAGES / NFM_TUNE_SEG override
 // the rule for tuning builds.
+template <class Op, class = void>
+struct three_mandatory : std::false_type {};
+template <class Op>
+struct three_mandatory<Op, std::void_t<decltype(Op::kThreeMandatory)>> : std::true_type {};
+
 template <class Op>
 struct TuneBase {
   using T = typename Op::scalar;
-  // operand 2 is the optional one in every op that has it
-  static constexpr int kInBytes = (((Op::kUse >> 0) & 1) * Op::kLen0 + ((Op::kUse >> 1) & 1) * Op::kLen1) * int(sizeof(T));
+  // operands 0 and 1 are mandatory wherever they are used, operand 2 is optional unless the op
+  // says so (kThreeMandatory), operand 3 is always optional: size the tiles for the mandatory ones
+  static constexpr int kInBytes =
+      (((Op::kUse >> 0) & 1) * Op::kLen0 + ((Op::kUse >> 1) & 1) * Op::kLen1 + (three_mandatory<Op>::value ? Op::kLen2 : 0)) * int(sizeof(T));
   static constexpr int kOutBytes = Op::kOut * int(sizeof(T));
   // Records that are a multiple of 32 B bank-conflict in the dense layout:
   // 2-way at 32 B, 4-way at 64 B, 8-way at 128 B.  The segmented layout removes
@@ -759,7 +803,7 @@ template <class Op>
 int launch_tail(const KParams& p, i64 done, cudaStream_t stream) {
   using T = typename Op::scalar;
   KParams q = p;
-  const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2};
+  const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2, len3<Op>::value};
   for (int i = 0; i < kMaxIn; ++i)
     if ((q.present >> i) & 1) q.in[i].ptr = static_cast<const T*>(q.in[i].ptr) + done * (q.in[i].stride == 0 ? 0 : lens[i]);
   q.out = static_cast<T*>(q.out) + done * Op::kOut;
@@ -771,7 +815,7 @@ int launch_tail(const KParams& p, i64 done, cudaStream_t stream) {
 
 // per (kernel instantiation, device, staged mask): resident CTAs per SM, 0 = not yet known
 struct LaunchCache {
-  std::atomic<int> per_sm[16][8];
+  std::atomic<int> per_sm[16][16];
   std::atomic<int> attr_set[16];
 };
 
@@ -798,7 +842,7 @@ int launch_tile(const KParams& p, cudaStream_t stream) {
   const int staged = staged_mask(p);
   auto smem_for = [](int mask) {
     const int stage = ((mask & 1) ? G::footprint(Op::kLen0) : 0) + ((mask & 2) ? G::footprint(Op::kLen1) : 0) +
-                      ((mask & 4) ? G::footprint(Op::kLen2) : 0);
+                      ((mask & 4) ? G::footprint(Op::kLen2) : 0) + ((mask & 8) ? G::footprint(len3<Op>::value) : 0);
     return STAGES * stage + 2 * G::kFootOut + STAGES * 8 + 16;
   };
   const int smem = smem_for(staged);
@@ -806,7 +850,7 @@ int launch_tile(const KParams& p, cudaStream_t stream) {
   if (smem > dev.max_smem_optin) return -1;  // caller falls back to the strided kernel
   const int d = current_device() & 15;
   if (!cache.attr_set[d].load(std::memory_order_acquire)) {
-    int most = smem_for(Op::kUse & 7);
+    int most = smem_for(Op::kUse & 15);
     if (most > dev.max_smem_optin) most = dev.max_smem_optin;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
     if (e != cudaSuccess) return int(e);
@@ -889,7 +933,7 @@ int run_op(KParams p, cudaStream_t stream) {
   constexpr int TILE = Tn::kThreads * Tn::kMpt;
   t_last_path_tma = 0;
   if (p.batch == 0) return NFM_OK;
-  const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2};
+  const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2, len3<Op>::value};
   bool fast = p.out_stride == Op::kOut && elem_stride(p.out_estride) == 1 && aligned16(p.out);
   int nstaged = 0;
   for (int i = 0; i < kMaxIn && fast; ++i) {
@@ -900,6 +944,42 @@ int run_op(KParams p, cudaStream_t stream) {
     ++nstaged;
   }
   if (fast && nstaged == 0) fast = false;
+  if (!fast && p.batch > 64) {
+    // Dense operands that only miss the 16-byte alignment (a view with a storage offset):
+    // peel the first h < 4 matrices so that every staged pointer becomes aligned, do those
+    // with the strided kernel and the rest on the TMA path.
+    bool dense = p.out_stride == Op::kOut && elem_stride(p.out_estride) == 1;
+    int any = 0;
+    for (int i = 0; i < kMaxIn && dense; ++i) {
+      if (!((p.present >> i) & 1)) continue;
+      if (elem_stride(p.in[i].estride) != 1 || (p.in[i].stride != 0 && p.in[i].stride != lens[i])) dense = false;
+      any += p.in[i].stride != 0;
+    }
+    if (dense && any > 0) {
+      constexpr int es = int(sizeof(typename Op::scalar));
+      for (int h = 1; h < 4; ++h) {
+        bool ok = (reinterpret_cast<uintptr_t>(p.out) + size_t(h) * Op::kOut * es) % 16 == 0;
+        for (int i = 0; i < kMaxIn && ok; ++i)
+          if (((p.present >> i) & 1) && p.in[i].stride != 0)
+            ok = (reinterpret_cast<uintptr_t>(p.in[i].ptr) + size_t(h) * lens[i] * es) % 16 == 0;
+        if (!ok) continue;
+        KParams head = p;
+        head.batch = h;
+        int rc = launch_strided<Op>(head, stream);
+        if (rc != 0) {
+          set_error("strided kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
+          return rc;
+        }
+        KParams rest = p;
+        for (int i = 0; i < kMaxIn; ++i)
+          if (((p.present >> i) & 1) && p.in[i].stride != 0)
+            rest.in[i].ptr = static_cast<const unsigned char*>(p.in[i].ptr) + size_t(h) * lens[i] * es;
+        rest.out = static_cast<unsigned char*>(p.out) + size_t(h) * Op::kOut * es;
+        rest.batch = p.batch - h;
+        return run_op<Op>(rest, stream);  // aligned now: takes the fast path
+      }
+    }
+  }
   if (fast) {
     // full tiles by TMA, the ragged remainder inside the same launch
     int rc;

@@ -110,8 +110,9 @@ struct SymSolveOp {
 };
 
 // Fused Gauss-Newton / Levenberg-Marquardt step:
-//   out = x - alpha * (A + lam I)^-1 v        in0 = mat (packed), in1 = v, in2 = x
-// i.e. sym_solve_ with a scalar regulariser followed by the update of the
+//   out = x - alpha * (A + lam I + diag(d))^-1 v     in0 = mat (packed), in1 = v, in2 = x, in3 = d (optional)
+// i.e. sym_solve_ with a scalar and / or per-voxel regulariser (the reference's
+// documented regulariser, _impl/sym.py:356-357) followed by the update of the
 // parameter field, without the round trip of the step through HBM.
 template <typename T, int N, int ALGO>
 struct SymSolveUpdateOp {
@@ -119,16 +120,18 @@ struct SymSolveUpdateOp {
   static constexpr int kLen0 = packed_len(N);
   static constexpr int kLen1 = N;
   static constexpr int kLen2 = N;
-  static constexpr int kUse = 7;
+  static constexpr int kLen3 = N;
+  static constexpr int kUse = 15;
   static constexpr int kOut = N;
   static constexpr bool kHeavy = false;
   static constexpr bool kScalars = true;
+  static constexpr bool kThreeMandatory = true;
 
-  __device__ static __forceinline__ void apply(const T (&m_in)[kLen0], const T (&v)[N], const T (&x0)[N], int present,
-                                               int flags, T lam, T alpha, T (&out)[N]) {
+  __device__ static __forceinline__ void apply(const T (&m_in)[kLen0], const T (&v)[N], const T (&x0)[N], const T (&reg)[N],
+                                               int present, int flags, T lam, T alpha, T (&out)[N]) {
     T m[kLen0];
 #pragma unroll
-    for (int k = 0; k < kLen0; ++k) m[k] = (k < N) ? m_in[k] + lam : m_in[k];
+    for (int k = 0; k < kLen0; ++k) m[k] = (k < N) ? m_in[k] + (lam + reg[k < N ? k : 0]) : m_in[k];
     T step[N];
     if constexpr (N <= 4) {
       sym_solve_closed<T, N>(m, v, step);
@@ -145,6 +148,78 @@ struct SymSolveUpdateOp {
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) out[i] = x0[i] - alpha * step[i];
+  }
+};
+
+// J^T H J (MODE 0) or J H J^T (MODE 1, K == D) in packed order; the register
+// kernel behind sym_matmul and the fused Gauss-Newton solve below
+// (_impl/sym.py:532-670)
+template <typename T, int K, int D, int MODE>
+__device__ __forceinline__ void sym_jhj(const T (&j)[K * D], const T (&h)[packed_len(MODE == 0 ? K : D)],
+                                        T (&out)[packed_len(MODE == 0 ? D : K)]) {
+  constexpr int HN = MODE == 0 ? K : D;  // order of H
+  constexpr int ON = MODE == 0 ? D : K;  // order of the result
+  // G = J as (ON x HN) "rows = output index": mode 0 uses J^T, mode 1 uses J
+  T hj[HN][ON];  // H * G^T
+#pragma unroll
+  for (int a = 0; a < HN; ++a)
+#pragma unroll
+    for (int o = 0; o < ON; ++o) {
+      T s = T(0);
+#pragma unroll
+      for (int b = 0; b < HN; ++b) {
+        const T g = MODE == 0 ? j[b * D + o] : j[o * D + b];
+        s += h[pidx(HN, a, b)] * g;
+      }
+      hj[a][o] = s;
+    }
+#pragma unroll
+  for (int o = 0; o < ON; ++o)
+#pragma unroll
+    for (int q = o; q < ON; ++q) {
+      T s = T(0);
+#pragma unroll
+      for (int a = 0; a < HN; ++a) {
+        const T g = MODE == 0 ? j[a * D + o] : j[o * D + a];
+        s += g * hj[a][q];
+      }
+      out[pidx(ON, o, q)] = s;
+    }
+}
+
+// Fused Gauss-Newton system: the packed Hessian
+// J^T H J (+ diag(d)) is built in registers and solved at once,
+//   x = (J^T H J + diag(d))^-1 g      in0 = J (K x D), in1 = H (packed), in2 = g, in3 = d (optional)
+// so the 6- / 21-coefficient Hessian field never goes to HBM and back
+// (reference chain: sym_matmul _impl/sym.py:637-670, then sym_solve :327-398).
+template <typename T, int K, int D, int MODE>
+struct SymMatmulSolveOp {
+  using scalar = T;
+  static constexpr int kHN = MODE == 0 ? K : D;
+  static constexpr int kON = MODE == 0 ? D : K;
+  static constexpr int kLen0 = K * D;
+  static constexpr int kLen1 = packed_len(kHN);
+  static constexpr int kLen2 = kON;
+  static constexpr int kLen3 = kON;
+  static constexpr int kUse = 15;
+  static constexpr int kOut = kON;
+  static constexpr bool kHeavy = false;
+  static constexpr bool kThreeMandatory = true;
+
+  __device__ static __forceinline__ void apply(const T (&j)[kLen0], const T (&h)[kLen1], const T (&g)[kON], const T (&reg)[kON],
+                                               int present, int flags, T (&x)[kON]) {
+    T a[packed_len(kON)];
+    sym_jhj<T, K, D, MODE>(j, h, a);
+#pragma unroll
+    for (int i = 0; i < kON; ++i) a[i] += reg[i];
+    if constexpr (kON <= 4) {
+      sym_solve_closed<T, kON>(a, g, x);
+    } else {
+      LDL<T, kON> f;
+      f.load_packed(a);
+      if (f.factor_checked()) f.solve(g, x);
+      else sym_solve_lu<T, kON>(a, g, x);
+    }
   }
 };
 

@@ -23,6 +23,7 @@ Signatures are the union of the reference's in-repo implementation
 """
 from __future__ import annotations
 
+import itertools
 import os
 from typing import Optional, Sequence, Union
 
@@ -39,7 +40,8 @@ __all__ = [
     'sym_submatvec', 'sym_submatvec_',
     'sym_solve', 'sym_solve_',
     'sym_invert', 'sym_invert_',
-    'sym_solve_update', 'sym_solve_update_',     # extension (not in the reference)
+    'sym_solve_update', 'sym_solve_update_',     # extensions (not in the reference): fused chains
+    'sym_matmul_solve',
 ]
 
 _METHODS = {None: _lib.ALGO_AUTO, 'auto': _lib.ALGO_AUTO, 'ldl': _lib.ALGO_LDL, 'chol': _lib.ALGO_LDL,
@@ -81,7 +83,7 @@ def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
         layout = D.detect_layout(nn, n)
         if inp is not None and inp.shape[-1] != n:
             raise ValueError("inp and vec must have the same trailing size")
-        res = out if out is not None else torch.empty_like(vec)
+        res = out if out is not None else D.empty_like_phased(vec)
         nb = vec.numel() // n
         if nb > 0:
             with D.device_of(vec.device):
@@ -126,6 +128,18 @@ def _matvec(inp: Optional[Tensor], mat: Tensor, vec: Tensor, sign: int,
             return out
         return r.cpu()
 
+    split = D.outer_split(batch, [(mat, 1), (vec, 1), (inp, 1)]) if nb > 0 else 0
+    if split:
+        # partially broadcast operands: one launch per index of the leading batch dims, on views
+        full = out if (out is not None and out.dtype == cdt and tuple(out.shape) == (*batch, n)) else \
+            torch.empty((*batch, n), dtype=cdt, device=dev)
+        for idx in itertools.product(*[range(k) for k in batch[:split]]):
+            _matvec(D.outer_views(inp, batch, 1, idx), D.outer_views(mat, batch, 1, idx),
+                    D.outer_views(vec, batch, 1, idx), sign, cdt, full[idx])
+        if out is not None and full is not out:
+            out.copy_(full)
+            return out
+        return full
     o, res, copy_back = D.out_operand(out, (*batch, n), 1, cdt, dev, allow_estride=True)
     if nb > 0:
         m = D.as_operand(mat, batch, 1, cdt, allow_estride=True)
@@ -267,7 +281,7 @@ def sym_solve(mat: Tensor, vec: Tensor,
         dev = vec.device
         reg = _as_diag(diag, n, vec.dtype, dev)
         if reg is None or reg.dim() == 1 or D.plain_cuda(vec, reg):
-            res = out if out is not None else torch.empty_like(vec)
+            res = out if out is not None else D.empty_like_phased(vec)
             nb = vec.numel() // n
             if nb > 0:
                 with D.device_of(dev):
@@ -315,6 +329,19 @@ def sym_solve(mat: Tensor, vec: Tensor,
             return out
         return r.cpu()
 
+    split = D.outer_split(batch, [(mat, 1), (vec, 1), (reg, 1)]) if nb > 0 else 0
+    if split:
+        # partially broadcast operands: one launch per index of the leading batch dims, on views
+        # (nothing is materialised; each launch sees dense / fully broadcast operands)
+        full = out if (out is not None and out.dtype == cdt and tuple(out.shape) == (*batch, n)) else \
+            torch.empty((*batch, n), dtype=cdt, device=dev)
+        for idx in itertools.product(*[range(k) for k in batch[:split]]):
+            sym_solve(D.outer_views(mat, batch, 1, idx), D.outer_views(vec, batch, 1, idx),
+                      D.outer_views(reg, batch, 1, idx), dtype=cdt, out=full[idx], method=method)
+        if out is not None and full is not out:
+            out.copy_(full)
+            return out
+        return full if (out is not None or full.dtype == res_dtype) else full.to(res_dtype)
     o, res, copy_back = D.out_operand(out if (out is None or out.dtype == cdt) else None, (*batch, n), 1, cdt, dev,
                                       allow_estride=True)
     if nb > 0:
@@ -347,13 +374,15 @@ def sym_solve_(mat: Tensor, vec: Tensor, diag=None, dtype: Optional[torch.dtype]
 # ---------------------------------------------------------------------------
 
 def sym_solve_update(x: Tensor, mat: Tensor, vec: Tensor, lam: float = 0.0, alpha: float = 1.0,
-                     out: Optional[Tensor] = None, *, method: Optional[str] = None) -> Tensor:
-    r"""``x - alpha * (mat + lam*I) \ vec`` in one pass over HBM.
+                     out: Optional[Tensor] = None, *, diag: Optional[Tensor] = None,
+                     method: Optional[str] = None) -> Tensor:
+    r"""``x - alpha * (mat + lam*I + diag(d)) \ vec`` in one pass over HBM.
 
     The Gauss-Newton / Levenberg-Marquardt update that otherwise is the chain
-    ``step = sym_solve(mat, vec, lam); x - alpha * step`` (reference names
+    ``step = sym_solve(mat, vec, lam + d); x - alpha * step`` (reference names
     sym.py:31-33); not a function of the reference.  CUDA tensors only;
-    ``mat (..., M*(M+1)//2)``, ``vec`` and ``x`` ``(..., M)`` with the same batch dims.
+    ``mat (..., M*(M+1)//2)``, ``vec`` and ``x`` ``(..., M)``; ``diag`` is the
+    reference's per-voxel regulariser ``(..., M)`` (or anything broadcastable to it).
     """
     x, mat, vec = torch.as_tensor(x), torch.as_tensor(mat), torch.as_tensor(vec)
     dev = D.common_device(x, mat, vec)
@@ -367,17 +396,21 @@ def sym_solve_update(x: Tensor, mat: Tensor, vec: Tensor, lam: float = 0.0, alph
     algo = _algo(method)
     if algo not in (_lib.ALGO_AUTO, _lib.ALGO_LDL):
         raise ValueError("sym_solve_update supports method 'auto' or 'ldl'")
-    batch = tuple(torch.broadcast_shapes(x.shape[:-1], mat.shape[:-1], vec.shape[:-1]))
+    reg = _as_diag(diag, n, cdt, dev)
+    shapes = [x.shape[:-1], mat.shape[:-1], vec.shape[:-1]] + ([reg.shape[:-1]] if reg is not None else [])
+    batch = tuple(torch.broadcast_shapes(*shapes))
     nb = D.batch_count(batch)
     o, res, copy_back = D.out_operand(out, (*batch, n), 1, cdt, dev)
     if nb > 0:
         m = D.as_operand(mat, batch, 1, cdt)
         v = D.as_operand(vec, batch, 1, cdt)
         xo = D.as_operand(x, batch, 1, cdt)
+        r = D.as_operand(reg, batch, 1, cdt) if reg is not None else None
         with D.device_of(dev):
-            rc = _lib.load().nfm_sym_solve_update(D.dtype_code(cdt), n, algo, nb, m.ptr, m.stride, v.ptr, v.stride,
-                                                  xo.ptr, xo.stride, float(lam), float(alpha), o.ptr, o.stride,
-                                                  D.current_stream_ptr(dev))
+            rc = _lib.load().nfm_sym_solve_update_reg(
+                D.dtype_code(cdt), n, algo, nb, m.ptr, m.stride, v.ptr, v.stride, xo.ptr, xo.stride,
+                None if r is None else r.ptr, 0 if r is None else r.stride, float(lam), float(alpha), o.ptr, o.stride,
+                D.current_stream_ptr(dev))
         _lib.check(rc, "nfm_sym_solve_update")
     if copy_back:
         res.copy_(o.tensor)
@@ -385,9 +418,54 @@ def sym_solve_update(x: Tensor, mat: Tensor, vec: Tensor, lam: float = 0.0, alph
 
 
 def sym_solve_update_(x: Tensor, mat: Tensor, vec: Tensor, lam: float = 0.0, alpha: float = 1.0, *,
-                      method: Optional[str] = None) -> Tensor:
-    r"""In-place ``x -= alpha * (mat + lam*I) \ vec``; returns ``x``."""
-    return sym_solve_update(x, mat, vec, lam, alpha, out=x, method=method)
+                      diag: Optional[Tensor] = None, method: Optional[str] = None) -> Tensor:
+    r"""In-place ``x -= alpha * (mat + lam*I + diag(d)) \ vec``; returns ``x``."""
+    return sym_solve_update(x, mat, vec, lam, alpha, out=x, diag=diag, method=method)
+
+
+def sym_matmul_solve(j: Tensor, h: Tensor, g: Tensor, diag=None, out: Optional[Tensor] = None) -> Tensor:
+    r"""``(J^T H J + diag(d)) \ g`` with the packed Hessian built and solved in registers.
+
+    The fused form of the Gauss-Newton chain ``sym_solve(sym_matmul(j, h), g, diag)``
+    (reference _impl/sym.py:637-670 then :327-398): the ``d*(d+1)//2``-coefficient Hessian
+    field is never written to memory.  ``j (..., k, d)``, ``h (..., k*(k+1)//2)`` or
+    diagonal ``(..., k)``, ``g (..., d)``, ``diag`` float / sequence / ``(..., d)``;
+    ``1 <= k, d <= 6``; CUDA tensors.  Like ``sym_matmul`` it evaluates ``J H J^T``
+    for ``k == d <= 3`` (the reference's unrolled branches).  Not a function of the reference.
+    """
+    j, h, g = torch.as_tensor(j), torch.as_tensor(h), torch.as_tensor(g)
+    dev = D.common_device(j, h, g)
+    if dev.type != "cuda":
+        raise RuntimeError("sym_matmul_solve takes CUDA tensors")
+    k, d = j.shape[-2:]
+    if not (1 <= k <= 6 and 1 <= d <= 6):
+        raise ValueError("sym_matmul_solve supports 1 <= k, d <= 6 (use sym_matmul + sym_solve above)")
+    if h.shape[-1] == k and k > 1:
+        h = torch.cat([h, h.new_zeros((*h.shape[:-1], k * (k - 1) // 2))], -1)
+    if h.shape[-1] != k * (k + 1) // 2:
+        raise ValueError("h must be compact symmetric (k*(k+1)//2 coefficients) or diagonal (k coefficients)")
+    mode = 1 if (k == d and k <= 3) else 0
+    if g.shape[-1] != d:
+        raise ValueError(f"g must have {d} trailing values")
+    cdt = D.compute_dtype(j, h, g)
+    reg = _as_diag(diag, d, cdt, dev)
+    shapes = [j.shape[:-2], h.shape[:-1], g.shape[:-1]] + ([reg.shape[:-1]] if reg is not None else [])
+    batch = tuple(torch.broadcast_shapes(*shapes))
+    nb = D.batch_count(batch)
+    o, res, copy_back = D.out_operand(out, (*batch, d), 1, cdt, dev)
+    if nb > 0:
+        jo = D.as_operand(j, batch, 2, cdt)
+        ho = D.as_operand(h, batch, 1, cdt)
+        go = D.as_operand(g, batch, 1, cdt)
+        r = D.as_operand(reg, batch, 1, cdt) if reg is not None else None
+        with D.device_of(dev):
+            rc = _lib.load().nfm_sym_matmul_solve(
+                D.dtype_code(cdt), k, d, mode, nb, jo.ptr, jo.stride, ho.ptr, ho.stride, go.ptr, go.stride,
+                None if r is None else r.ptr, 0 if r is None else r.stride, o.ptr, o.stride, D.current_stream_ptr(dev))
+        _lib.check(rc, "nfm_sym_matmul_solve")
+    if copy_back:
+        res.copy_(o.tensor)
+    return res
 
 
 # ---------------------------------------------------------------------------
@@ -416,7 +494,8 @@ def sym_invert(mat: Tensor, diag: bool = False, dtype: Optional[torch.dtype] = N
         n = D.packed_order(nn)
         _check_n(n)
         no = n if diag else nn
-        res = out if out is not None else torch.empty((*mat.shape[:-1], no), dtype=mat.dtype, device=mat.device)
+        res = out if out is not None else (D.empty_like_phased(mat) if no == nn else
+                                           torch.empty((*mat.shape[:-1], no), dtype=mat.dtype, device=mat.device))
         nb = mat.numel() // nn
         if nb > 0:
             with D.device_of(mat.device):

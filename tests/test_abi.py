@@ -75,3 +75,37 @@ def test_header_is_plain_c():
     r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", HEADER],
                        capture_output=True, text=True)
     assert r.returncode == 0 and r.stderr.strip() == "", r.stderr
+
+
+def _build_c_caller(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.isfile(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("no CUDA toolkit headers")
+    exe = str(tmp_path / "abi_c_call")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-O1", os.path.join(ROOT, "tests", "abi_c_call.c"), "-o", exe,
+                        "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+                        "-L" + libdir, "-l:libnfm_sm100a.so", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+                        "-Wl,-rpath," + libdir + ",-rpath," + os.path.join(cuda, "lib64")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_program_links_against_the_abi(tmp_path):
+    """tests/abi_c_call.c (plain C99, no Python in between) compiles and links
+    against include/nfm.h + libnfm_sm100a.so."""
+    _build_c_caller(tmp_path)
+
+
+@pytest.mark.gpu
+def test_c_program_calls_the_abi(tmp_path):
+    """... and, on the GPU box, runs: cudaMalloc buffers, nfm_sym_solve -> nfm_sym_matvec
+    round trip checked on the host, error codes for bad arguments."""
+    import subprocess
+    exe = _build_c_caller(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), (r.returncode, r.stdout, r.stderr)

@@ -567,12 +567,22 @@ def test_reference_test_batchmatvec(nfm):
 
 
 def test_reference_test_batchdet_and_inv(nfm):
-    g = torch.Generator(device=DEV).manual_seed(0)
-    for n in (1, 2, 3, 4):
-        mat = torch.randn(2, n, n, device=DEV, generator=g)
-        assert torch.allclose(nfm.batchdet(mat), torch.det(mat.cpu()).to(DEV), rtol=1e-4, atol=1e-6), n
-        mat.diagonal(0, -1, -2).add_(10)
-        assert torch.allclose(nfm.batchinv(mat), torch.linalg.inv(mat.cpu()).to(DEV)), n
+    """tests/test_batched.py:44-97 of the reference at ITS tolerance (default allclose:
+    rtol 1e-5, atol 1e-8, fp32, against torch on the same device).  The reference draws
+    unseeded randn(2, n, n); two different fp32 algorithms cannot agree to 1e-5 on a
+    nearly singular draw, so here ten seeded draws are made and those with a condition
+    number below 30 (most of them) must pass -- at least half of the draws are checked."""
+    checked = 0
+    for seed in range(10):
+        g = torch.Generator(device=DEV).manual_seed(seed)
+        for n in (1, 2, 3, 4):
+            mat = torch.randn(2, n, n, device=DEV, generator=g)
+            if float(torch.linalg.cond(mat.double()).max()) < 30:
+                checked += 1
+                assert torch.allclose(nfm.batchdet(mat), torch.det(mat)), (seed, n)
+            mat.diagonal(0, -1, -2).add_(10)
+            assert torch.allclose(nfm.batchinv(mat), torch.linalg.inv(mat)), (seed, n)
+    assert checked >= 20, checked
 
 
 # --------------------------------------------------------------------------
@@ -603,35 +613,51 @@ def test_full_size_round_trip(nfm, n, side):
     assert err < 2e-5, err
     x2 = nfm.sym_solve(mat, 2 * vec)
     assert ((x2 - 2 * x).norm(dim=-1) / x.norm(dim=-1)).max().item() < 1e-6
-    if n <= 6:
-        inv = nfm.sym_invert(mat)
-        again = nfm.sym_invert(inv)
-        assert ((again - mat).norm(dim=-1) / mat.norm(dim=-1)).max().item() < 5e-5
-        # slab parity against the oracle on a slice the CPU finishes in seconds
-        sl = slice(batch // 2, batch // 2 + 50000)
-        close(x[sl], P.sym_solve(mat[sl].cpu(), vec[sl].cpu()), dtype)
-        close(inv[sl], P.sym_invert(mat[sl].cpu()), dtype)
+    # slab parity against the oracle on a slice the CPU finishes in seconds
+    sl = slice(batch // 2, batch // 2 + (50000 if n <= 6 else 20000))
+    want = P.sym_solve(mat[sl].cpu(), vec[sl].cpu())
+    close(x[sl], want, dtype)
+    if n > 4:
+        # the north star's nominal path for N > 4 (sub-warp shuffle kernel) and pivoted LU, at full size
+        xw = nfm.sym_solve(mat, vec, method="warp")
+        assert ((xw - x).norm(dim=-1) / x.norm(dim=-1)).max().item() < 5e-6
+        close(xw[sl], want, dtype)
+        xl = nfm.sym_solve(mat, vec, method="lu")
+        assert ((xl - x).norm(dim=-1) / x.norm(dim=-1)).max().item() < 5e-6
+        del xw, xl
+    inv = nfm.sym_invert(mat)
+    again = nfm.sym_invert(inv)
+    assert ((again - mat).norm(dim=-1) / mat.norm(dim=-1)).max().item() < 5e-5
+    isl = slice(batch // 2, batch // 2 + (50000 if n <= 6 else 4000))    # the reference inverts with N solves: slow on the CPU
+    close(inv[isl], P.sym_invert(mat[isl].cpu()), dtype)
 
 
 def test_config4_dense_fp64(nfm):
-    """config 4 (general 4x4 fp64), at 8M of the 64M batch: A A^-1 = I,
-    det(A^-1) = 1/det(A), solve residual."""
-    n, batch = 4, 8 << 20
+    """config 4 (general 4x4 fp64) at its full size, 64 Mi matrices (8.6 GB in, 8.6 GB out):
+    A A^-1 = I, det(A^-1) = 1/det(A), solve residual, oracle on slices."""
+    n, batch = 4, 64 << 20
     g = torch.Generator(device=DEV).manual_seed(4)
     a = torch.randn(batch, n, n, device=DEV, dtype=torch.float64, generator=g)
     a.diagonal(0, -1, -2).add_(10)
     b = torch.randn(batch, n, device=DEV, dtype=torch.float64, generator=g)
     inv = nfm.batchinv(a)
     eye = torch.eye(n, device=DEV, dtype=torch.float64)
-    assert (a @ inv - eye).abs().max().item() < 1e-13
+    worst = 0.0
+    for c in range(0, batch, 8 << 20):                      # in chunks: a @ inv of the whole batch would take 8.6 GB more
+        worst = max(worst, (a[c:c + (8 << 20)] @ inv[c:c + (8 << 20)] - eye).abs().max().item())
+    assert worst < 1e-13, worst
     d, di = nfm.batchdet(a), nfm.batchdet(inv)
     assert (d * di - 1).abs().max().item() < 1e-12
     x = nfm.solvevec(a, b)
-    assert ((a @ x[..., None])[..., 0] - b).abs().max().item() < 1e-12
-    sl = slice(12345, 12345 + 100000)
-    close(inv[sl], P.batchinv(a[sl].cpu()), torch.float64, 2)
-    close(d[sl], P.batchdet(a[sl].cpu()), torch.float64, 0)
-    close(x[sl], P.solvevec(a[sl].cpu(), b[sl].cpu()), torch.float64)
+    worst = 0.0
+    for c in range(0, batch, 8 << 20):
+        worst = max(worst, ((a[c:c + (8 << 20)] @ x[c:c + (8 << 20), :, None])[..., 0] - b[c:c + (8 << 20)]).abs().max().item())
+    assert worst < 1e-12, worst
+    for start in (12345, batch // 2 + 7, batch - 100000):   # first slab, middle, the very end
+        sl = slice(start, start + 100000)
+        close(inv[sl], P.batchinv(a[sl].cpu()), torch.float64, 2)
+        close(d[sl], P.batchdet(a[sl].cpu()), torch.float64, 0)
+        close(x[sl], P.solvevec(a[sl].cpu(), b[sl].cpu()), torch.float64)
 
 
 # --------------------------------------------------------------------------
@@ -903,3 +929,110 @@ def test_fused_solve_update(nfm, dtype, n):
     assert nfm.sym_solve_update_(xd, mat.to(DEV), vec.to(DEV), 0.3, 0.5).data_ptr() == xd.data_ptr()
     num = (xd.cpu().double() - want.double()).norm(dim=-1)
     assert float((num / den).max()) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [2, 3, 6, 10])
+def test_fused_solve_update_per_voxel_regulariser(nfm, dtype, n):
+    """The reference's documented regulariser (_impl/sym.py:356-357) as a fourth staged
+    operand of the fused update: x - alpha (A + lam I + diag(d))^-1 v  ==  the oracle chain."""
+    batch = 30_011
+    mat = G.spd_packed(batch, n, dtype, seed=n)
+    vec = G.vectors(batch, n, dtype, seed=n + 1)
+    x = G.vectors(batch, n, dtype, seed=n + 2)
+    reg = G.vectors(batch, n, dtype, seed=n + 3).abs()
+    lam, alpha = 0.25, 0.5
+    step = P.sym_solve(mat, vec, reg + lam)
+    want = x - alpha * step
+    den = (x.double().norm(dim=-1) + alpha * step.double().norm(dim=-1)).clamp_min(1e-300)
+    dm, dv, dx, dr = (t.to(DEV) for t in (mat, vec, x, reg))
+    for kw in (dict(diag=dr), dict(diag=dr[:1].expand(batch, n) * 0 + dr), dict(diag=dr, out=torch.empty_like(dx))):
+        got = nfm.sym_solve_update(dx, dm, dv, lam, alpha, **kw)
+        assert float(((got.cpu().double() - want.double()).norm(dim=-1) / den).max()) <= TOL[dtype]
+    # one (n,) regulariser broadcast to the whole field, and a shape-(1,) tensor
+    r1 = reg[0]
+    want1 = x - alpha * P.sym_solve(mat, vec, r1 + lam)
+    got1 = nfm.sym_solve_update(dx, dm, dv, lam, alpha, diag=r1.to(DEV))
+    assert float(((got1.cpu().double() - want1.double()).norm(dim=-1) / den).max()) <= TOL[dtype] * 2
+    close(nfm.sym_solve(dm, dv, torch.tensor([0.125], device=DEV, dtype=dtype)), P.sym_solve(mat, vec, 0.125), dtype)
+    strided = torch.arange(2 * n, device=DEV, dtype=dtype)[::2] * 0.01 + 0.1       # ADVICE r1: non-contiguous 1-D diag
+    close(nfm.sym_solve(dm, dv, strided), P.sym_solve(mat, vec, strided.cpu()), dtype)
+    xd = dx.clone()
+    assert nfm.sym_solve_update_(xd, dm, dv, lam, alpha, diag=dr).data_ptr() == xd.data_ptr()
+    assert float(((xd.cpu().double() - want.double()).norm(dim=-1) / den).max()) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fused_matmul_solve(nfm, dtype):
+    """(J^T H J + diag(d))^-1 g built and solved in registers == the oracle chain
+    sym_matmul -> sym_solve (reference _impl/sym.py:637-670 then :327-398), including
+    the reference's J H J^T for k == d <= 3."""
+    batch = 20_011
+    for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (6, 6), (2, 3), (3, 2), (4, 3), (6, 3), (3, 6), (5, 6), (6, 5)]:
+        j = G.vectors((batch, k), d, dtype, seed=k * 10 + d)
+        j = 0.3 * j + 2 * torch.eye(k, d, dtype=dtype)    # singular values in about [1, 3]: J^T H J well conditioned when k >= d
+        h = G.spd_packed(batch, k, dtype, seed=k)
+        g = G.vectors(batch, d, dtype, seed=k + d)
+        reg = G.vectors(batch, d, dtype, seed=k + d + 1).abs() + (1.0 if k < d else 0.0)   # k < d: J^T H J is singular
+        a = P.sym_matmul(j, h)
+        dj, dh, dg, dr = (t.to(DEV) for t in (j, h, g, reg))
+        close(nfm.sym_matmul(dj, dh), a, dtype, scale=4)
+        close(nfm.sym_matmul_solve(dj, dh, dg, dr), P.sym_solve(a, g, reg), dtype, scale=10)
+        if k >= d:
+            close(nfm.sym_matmul_solve(dj, dh, dg), P.sym_solve(a, g), dtype, scale=10)
+        # diagonal Hessian (reference jhjn accepts it) and a scalar regulariser
+        hd = h[..., :k].contiguous()
+        if not (k == d and k <= 3):
+            ad = P.full_to_sym(j.transpose(-1, -2) @ torch.diag_embed(hd) @ j)
+            close(nfm.sym_matmul(dj, hd.to(DEV)), ad, dtype, scale=4)
+            close(nfm.sym_matmul_solve(dj, hd.to(DEV), dg, 0.5), P.sym_solve(ad, g, 0.5), dtype, scale=10)
+    # broadcasting: one Jacobian for the whole field
+    j1 = torch.eye(3, dtype=dtype) * 1.5
+    h = G.spd_packed(batch, 3, dtype, seed=3)
+    g = G.vectors(batch, 3, dtype, seed=9)
+    close(nfm.sym_matmul_solve(j1.to(DEV), h.to(DEV), g.to(DEV)), P.sym_solve(P.sym_matmul(j1.expand(batch, 3, 3), h), g), dtype, scale=10)
+
+
+def test_partially_broadcast_operands_are_not_materialised(nfm):
+    """One Hessian field for a batch of gradient fields (and the other way round): the leading
+    batch dims are looped over with one launch each, on views -- no operand is copied."""
+    from nitorch_fastmath_b200 import _lib
+    dtype, n = torch.float32, 3
+    b, x, y = 3, 40, 50
+    mat1 = G.spd_packed((1, x, y), n, dtype, seed=1)           # (1, X, Y, 6): shared by the batch
+    vec = G.vectors((b, x, y), n, dtype, seed=2)               # (B, X, Y, 3)
+    want = P.sym_solve(mat1.expand(b, x, y, -1).contiguous(), vec)
+    before = _lib.launch_count()
+    got = nfm.sym_solve(mat1.to(DEV), vec.to(DEV))
+    assert _lib.launch_count() - before == b                   # one launch per outer index, each on the TMA path
+    assert _lib.load().nfm_last_path_was_tma() == 1
+    close(got, want, dtype)
+    close(nfm.sym_matvec(mat1.to(DEV), vec.to(DEV)), P.sym_matvec(mat1.expand(b, x, y, -1).contiguous(), vec), dtype)
+    # per-image matrices, one vector field: (B, 1, 1, 6) with (1, X, Y, 3); and a regulariser field (1, X, Y, 3)
+    matb = G.spd_packed((b, 1, 1), n, dtype, seed=3)
+    vec1 = G.vectors((1, x, y), n, dtype, seed=4)
+    reg1 = G.vectors((1, x, y), n, dtype, seed=5).abs()
+    want = P.sym_solve(matb.expand(b, x, y, -1).contiguous(), vec1.expand(b, x, y, -1).contiguous(),
+                       reg1.expand(b, x, y, -1).contiguous())
+    out = torch.empty(b, x, y, n, device=DEV, dtype=dtype)
+    assert nfm.sym_solve(matb.to(DEV), vec1.to(DEV), reg1.to(DEV), out=out) is out
+    close(out, want, dtype)
+
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_storage_offset_views_take_the_tma_path(nfm, n):
+    """A dense view that starts one record into its storage is not 16-byte aligned; the first
+    h < 4 matrices are peeled off (strided kernel) so that the rest is, and goes by TMA."""
+    from nitorch_fastmath_b200 import _lib
+    dtype, batch = torch.float32, 200_001
+    mat = G.spd_packed(batch + 1, n, dtype, seed=n).to(DEV)
+    vec = G.vectors(batch + 1, n, dtype, seed=n + 1).to(DEV)
+    assert mat[1:].data_ptr() % 16 != 0 or vec[1:].data_ptr() % 16 != 0
+    before = _lib.launch_count()
+    x = nfm.sym_solve(mat[1:], vec[1:])
+    assert _lib.load().nfm_last_path_was_tma() == 1
+    assert _lib.launch_count() - before <= 3          # head, tiles (+ the < 4-matrix tail)
+    close(x, P.sym_solve(mat[1:].cpu(), vec[1:].cpu()), dtype)
+    assert torch.equal(x, nfm.sym_solve(mat[1:].clone(), vec[1:].clone()))
+    inv = nfm.sym_invert(mat[1:])
+    close(inv, P.sym_invert(mat[1:].cpu()), dtype)
