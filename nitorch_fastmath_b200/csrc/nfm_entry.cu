@@ -201,6 +201,7 @@ int nfm_sym_invert_ex(int dtype, int n, int algo, int diag_only, int64_t batch, 
   int rc = NFM_OK;
   if (!check_common(dtype, n, batch, rc)) return rc;
   if (algo < NFM_ALGO_AUTO || algo > NFM_ALGO_WARP) return fail(NFM_E_UNSUPPORTED, "unknown algo");
+  if (algo == NFM_ALGO_WARP) return fail(NFM_E_UNSUPPORTED, "sym_invert has no sub-warp variant (NFM_ALGO_WARP is a sym_solve A/B kernel)");
   Args a;
   a.in(0, mat, true);
   a.out(out);
@@ -211,7 +212,7 @@ int nfm_sym_invert_ex(int dtype, int n, int algo, int diag_only, int64_t batch, 
     return finish(dtype == NFM_F32 ? sym_invert_part1<float>(n, diag_only, a.p, s) : sym_invert_part1<double>(n, diag_only, a.p, s));
   if (algo == NFM_ALGO_AUTO && n > 4)
     return finish(dtype == NFM_F32 ? sym_invert_part2<float>(n, diag_only, a.p, s) : sym_invert_part2<double>(n, diag_only, a.p, s));
-  // N <= 4 closed forms; NFM_ALGO_LDL; NFM_ALGO_WARP has no invert kernel: plain LDL^T
+  // N <= 4 closed forms; NFM_ALGO_LDL
   return finish(dtype == NFM_F32 ? sym_invert_part0<float>(n, diag_only, a.p, s) : sym_invert_part0<double>(n, diag_only, a.p, s));
 }
 

@@ -252,7 +252,8 @@ def sym_solve(mat: Tensor, vec: Tensor,
     check and a pivoted-LU fallback, so SPD fields run at LDL^T speed and
     indefinite matrices get the reference's semantics.  ``method='ldl'``:
     unchecked LDL^T; ``'lu'``: partial pivoting for every matrix (what the
-    reference does); ``'warp'``: the sub-warp cooperative A/B variant.
+    reference does); ``'warp'``: the sub-warp cooperative A/B variant (LDL^T with
+    shuffles, no pivoting: SPD input only; several times slower, kept for comparison).
 
     Parameters
     ----------
@@ -488,6 +489,8 @@ def sym_invert(mat: Tensor, diag: bool = False, dtype: Optional[torch.dtype] = N
     -------
     imat : `(..., M or M*(M+1)//2) tensor` (compact storage, same ordering)
     """
+    if _algo(method) == _lib.ALGO_WARP:
+        raise ValueError("method='warp' is a sym_solve A/B kernel (SPD input, no pivoting); sym_invert has no such variant")
     if dtype is None and torch.is_tensor(mat) and D.plain_cuda(mat) and (
             out is None or (D.plain_cuda(mat, out) and out.shape[-1] == (D.packed_order(mat.shape[-1]) if diag else mat.shape[-1]))):
         nn = mat.shape[-1]
