@@ -28,7 +28,6 @@ import json
 import math
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -226,50 +225,90 @@ def bind_to_gpu_cpus(index: int):
 # clocks during the timed region (NVML)
 # --------------------------------------------------------------------------
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+period = float(sys.argv[2])
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    t = time.time()
+    try:
+        print(t, nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(h), flush=True)
+    except Exception:
+        pass
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region, polled from NVML by a separate
+    PROCESS (a sampling thread in this process would fight the launch loop for the GIL: with
+    20 steps of 16 us the timed region is 0.3 ms long).  Start it well before the region
+    (``start()``), bracket the region with ``with sampler:``; samples are matched by wall clock.
+    Regions shorter than the NVML polling period also take the samples just before / after."""
     REASONS = {
         0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
         0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
         0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period: float = 0.002):
+    def __init__(self, index: int, period: float = 0.0005):
+        import subprocess
+        import tempfile
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thread = None
+        self._t0 = self._t1 = None
+        self._out = tempfile.NamedTemporaryFile("w+", suffix=".clocks", delete=False)
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self._nv = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
-            self._period = period
+            self._proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index), str(period)],
+                                          stdout=self._out, stderr=subprocess.DEVNULL)
         except Exception:
-            self._nv = None
+            self._proc = None
 
-    def _run(self):
-        nv = self._nv
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(self._period)
+    def wait_ready(self, timeout: float = 10.0):
+        """Block until the sampler process has produced its first sample (it imports pynvml first)."""
+        t_end = time.time() + timeout
+        while self._proc is not None and time.time() < t_end:
+            if os.path.getsize(self._out.name) > 40:
+                return
+            time.sleep(0.01)
 
     def __enter__(self):
-        if self._nv is not None:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
+        self._t0 = time.time()
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        if self._thread is not None:
-            self._thread.join()
+        self._t1 = time.time()
+        time.sleep(0.003)          # let the sampler take one more sample after the region
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+        rows = []
+        try:
+            with open(self._out.name) as f:
+                for line in f:
+                    p = line.split()
+                    if len(p) == 2 and p[0] == "max":
+                        self.max_mhz = int(p[1])
+                    elif len(p) == 3:
+                        rows.append((float(p[0]), int(p[1]), int(p[2])))
+            os.unlink(self._out.name)
+        except Exception:
+            pass
+        inside = [r for r in rows if self._t0 <= r[0] <= self._t1]
+        if len(inside) < 3:        # very short region: the samples that bracket it
+            before = [r for r in rows if r[0] < self._t0][-2:]
+            after = [r for r in rows if r[0] > self._t1][:2]
+            inside = before + inside + after
+        for _, mhz, mask in inside:
+            self.samples.append(mhz)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
 
     def summary(self):
         s = sorted(self.samples)
@@ -450,17 +489,24 @@ def run_workload(args, rank, local_rank, world, dist):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    clocks = ClockSampler(local_rank)
     for i in range(args.warmup):
         step(i)
+    clocks.wait_ready()
+    # the timed loop is as tight as Python allows: pre-bound C-ABI calls, return codes checked afterwards
+    seq = [launchers[(args.warmup + i) % nsets] for i in range(args.steps)]
     sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.launch_count()
-    with ClockSampler(local_rank) as clocks:
+    rc_any = 0
+    with clocks:
         ev0.record()
-        for i in range(args.steps):
-            step(i)
+        for f in seq:
+            rc_any |= f()
         ev1.record()
         sync()
+    if rc_any:
+        _lib.check(rc_any, "bench step")
     launches = _lib.launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     if dist is not None:
