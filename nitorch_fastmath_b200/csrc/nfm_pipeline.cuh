@@ -735,7 +735,8 @@ struct Tune : TuneRule<Op> {};
 // config 1): several small CTAs per SM ramp up and drain faster than one big one.
 // Measured with the L2 prefetch in place (profiles/r2_geometry_sweep.txt):
 //   records <= 64 B  (3x3 solve): 256 threads x 2, 2 stages -- 8.4 vs 10.4 us at 1M,
-//       15.7 vs 18.2 us at 2M, 31.0 vs 32.9 us at 4M, equal at 8M matrices
+//       15.7 vs 18.2 us at 2M, 31.0 vs 32.9 us at 4M, equal at 8M matrices (the write-heavy
+//       3x3 invert already loses there: 0.88 vs 0.95 of the peak)
 //   records <= 200 B (6x6 solve / invert): 128 threads x 1, 3 stages -- 18.2 vs 19.3 us and
 //       24.9 vs 25.4 us at 885k matrices, behind the large geometry from ~1.5M
 // `kBelowBytes`: use it when the launch moves fewer algorithmic bytes than this.
@@ -744,9 +745,12 @@ struct TuneSmall {
   using B = TuneBase<Op>;
   static constexpr int kRec = B::kInBytes + B::kOutBytes;
   static constexpr bool kTiny = kRec <= 64;
-  static constexpr bool kEnabled = !Op::kHeavy && ((kTiny && Tune<Op>::kTile >= 1024) || (!kTiny && kRec <= 200 && Tune<Op>::kTile > 128));
+  // (records below 20 B of input keep the large tiles: 512 of them are bulk copies of 2-4 KB, and the
+  //  order-1/2 routines lost 10-25 % with them, profiles/r2_sweep_all_orders_f32.txt first pass)
+  static constexpr bool kEnabled = !Op::kHeavy && B::kInBytes >= 20 &&
+                                   ((kTiny && Tune<Op>::kTile >= 1024) || (!kTiny && kRec <= 200 && Tune<Op>::kTile > 128));
   static constexpr int kThreads = kTiny ? 256 : 128, kMpt = kTiny ? 2 : 1, kStages = kTiny ? 2 : 3;
-  static constexpr long long kBelowBytes = kTiny ? (400ll << 20) : (180ll << 20);
+  static constexpr long long kBelowBytes = kTiny ? (300ll << 20) : (180ll << 20);
 };
 
 // Pool geometry for compute-heavy ops with large records (pool_kernel).
