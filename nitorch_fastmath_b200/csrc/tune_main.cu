@@ -599,6 +599,40 @@ int main(int argc, char** argv) {
     CFG(Op, "dense_inv4d", 128, 1, 3, true, 256);
     release(buf);
   }
+  if (want("reps20")) {
+    // what a 20-launch timed region costs per launch against a long one (the driver's protocol at 8 GPUs)
+    using Op = SymSolveOp<float, 3, NFM_LAYOUT_SYM, 0>;
+    Buffers buf = make<float>(256ll * 256 * 256, 6, 3, 3, 3);
+    const i64 sub = i64(1) << 21;
+    std::vector<KParams> ps(8);
+    for (int s = 0; s < 8; ++s) {
+      KParams p{};
+      p.in[0].ptr = static_cast<const float*>(buf.in0) + i64(s) * sub * 6;
+      p.in[0].stride = 6;
+      p.in[1].ptr = static_cast<const float*>(buf.in1) + i64(s) * sub * 3;
+      p.in[1].stride = 3;
+      p.present = 3;
+      p.out = static_cast<float*>(buf.out) + i64(s) * sub * 3;
+      p.out_stride = 3;
+      p.batch = sub;
+      ps[s] = p;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int reps : {20, 20, 20, 200, 200, 20, 20}) {
+      for (int i = 0; i < 8; ++i) launch_tile<Op, 256, 2, 2, false>(ps[i], 0);
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0);
+      for (int i = 0; i < reps; ++i) launch_tile<Op, 256, 2, 2, false>(ps[i % 8], 0);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      printf("C++ loop, 2M-matrix launches, %3d in the timed region: %.2f us per launch (%.1f us total)\n", reps, ms * 1e3 / reps, ms * 1e3);
+    }
+    release(buf);
+  }
   if (want("det4d")) {
     using Op = BatchDetOp<double, 4>;
     Buffers buf = make<double>(16ll << 20, 16, -4, 0, 1);
