@@ -129,6 +129,15 @@ int nfm_batch_solve(int dtype, int n, int nrhs, int algo, int64_t batch,
                     const void *b, int64_t b_stride,
                     void *out, int64_t out_stride, void *stream);
 
+/* X = B A^-1 (right division) ; A: n x n row-major, B and X: nrows x n row-major
+ * records -- solved as A^T x_r = b_r for every row r, without transposed copies.
+ * Replaces: sugar.rmdiv  sugar.py:140-191 (documented meaning A x B^-1; as written
+ * the reference returns (B^-1 A)^T). */
+int nfm_batch_rsolve(int dtype, int n, int nrows, int algo, int64_t batch,
+                     const void *a, int64_t a_stride,
+                     const void *b, int64_t b_stride,
+                     void *out, int64_t out_stride, void *stream);
+
 /* y = A v ; A: m x n row-major, v: n, y: m.
  * Replaces: batchmatvec  _impl/batched.py:154-190. */
 int nfm_batch_matvec(int dtype, int m, int n, int64_t batch,

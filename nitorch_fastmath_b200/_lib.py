@@ -43,6 +43,7 @@ SIGNATURES = {
     "nfm_batch_inv": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P]),
     "nfm_batch_det": (c_int, [_I, _I, _L, _P, _L, _P, _L, _P]),
     "nfm_batch_solve": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P]),
+    "nfm_batch_rsolve": (c_int, [_I, _I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P]),
     "nfm_batch_matvec": (c_int, [_I, _I, _I, _L, _P, _L, _P, _L, _P, _L, _P]),
     "nfm_sym_det": (c_int, [_I, _I, _L, _P, _L, _P, _L, _P]),
     "nfm_sym_to_full": (c_int, [_I, _I, _L, _P, _L, _P, _L, _P]),

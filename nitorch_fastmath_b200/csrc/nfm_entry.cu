@@ -277,8 +277,8 @@ int nfm_batch_solve(int dtype, int n, int nrhs, int algo, int64_t batch, const v
     if (mat == nullptr || b == nullptr || out == nullptr) return fail(NFM_E_BADARG, "NULL operand");
     if (a_stride < 0 || b_stride < 0 || out_stride < 0) return fail(NFM_E_BADARG, "negative batch stride");
     const int chol = algo == NFM_ALGO_LDL;
-    rc = dtype == NFM_F32 ? batch_solve_rt<float>(n, nrhs, chol, batch, mat, a_stride, b, b_stride, out, out_stride, s)
-                          : batch_solve_rt<double>(n, nrhs, chol, batch, mat, a_stride, b, b_stride, out, out_stride, s);
+    rc = dtype == NFM_F32 ? batch_solve_many<float>(n, nrhs, chol, 0, batch, mat, a_stride, b, b_stride, out, out_stride, s)
+                          : batch_solve_many<double>(n, nrhs, chol, 0, batch, mat, a_stride, b, b_stride, out, out_stride, s);
     if (rc) set_error("solve kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
     return rc;
   }
@@ -291,6 +291,23 @@ int nfm_batch_solve(int dtype, int n, int nrhs, int algo, int64_t batch, const v
   if (algo == NFM_ALGO_LDL)
     return finish(dtype == NFM_F32 ? batch_solve_ldl_impl<float>(n, a.p, s) : batch_solve_ldl_impl<double>(n, a.p, s));
   return finish(dtype == NFM_F32 ? batch_solve_lu_impl<float>(n, a.p, s) : batch_solve_lu_impl<double>(n, a.p, s));
+}
+
+int nfm_batch_rsolve(int dtype, int n, int nrows, int algo, int64_t batch, const void* mat, int64_t a_stride, const void* b,
+                     int64_t b_stride, void* out, int64_t out_stride, void* stream) {
+  int rc = NFM_OK;
+  if (!check_common(dtype, n, batch, rc)) return rc;
+  if (nrows < 1) return fail(NFM_E_BADARG, "nrows must be >= 1");
+  if (algo == NFM_ALGO_AUTO) algo = NFM_ALGO_LU;
+  if (algo != NFM_ALGO_LU && algo != NFM_ALGO_LDL) return fail(NFM_E_UNSUPPORTED, "batch_rsolve: algo must be LU or LDL");
+  if (mat == nullptr || b == nullptr || out == nullptr) return fail(NFM_E_BADARG, "NULL operand");
+  if (a_stride < 0 || b_stride < 0 || out_stride < 0) return fail(NFM_E_BADARG, "negative batch stride");
+  auto s = static_cast<cudaStream_t>(stream);
+  const int chol = algo == NFM_ALGO_LDL;
+  rc = dtype == NFM_F32 ? batch_solve_many<float>(n, nrows, chol, 1, batch, mat, a_stride, b, b_stride, out, out_stride, s)
+                        : batch_solve_many<double>(n, nrows, chol, 1, batch, mat, a_stride, b, b_stride, out, out_stride, s);
+  if (rc) set_error("solve kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
+  return rc;
 }
 
 int nfm_batch_matvec(int dtype, int m, int n, int64_t batch, const void* mat, int64_t mat_stride, const void* vec,

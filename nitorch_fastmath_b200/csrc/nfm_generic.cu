@@ -85,6 +85,129 @@ __global__ void __launch_bounds__(128) solve_rt_kernel(const T* mat, i64 as, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// Many right-hand sides (nrhs > 4) and right division: the factorisation lives in
+// REGISTERS (compile-time order N, static indices), the right-hand sides are a
+// run-time loop.  One thread per matrix, straight from global memory: each thread
+// walks its own contiguous records, whose lines stay in L1 between columns.
+//   left  (right == 0): X = A^-1 B,  B and X  n x nrhs row-major  (column c: b[i*nrhs + c])
+//   right (right == 1): X = B A^-1,  B and X  nrhs x n row-major  (row c: b[c*n + i]), i.e.
+//                       A^T x_c = b_c for every row c -- no transposed copies of A or B.
+// LU with partial pivoting keeps the multipliers in the lower triangle and the pivot
+// rows in piv[]; a column replays the exchanges with predicated swaps (skipped by a
+// warp vote when no matrix of the warp pivoted in that step).
+// ---------------------------------------------------------------------------
+template <typename T, int N, bool CHOL>
+__global__ void __launch_bounds__(128) solve_many_kernel(const T* mat, i64 as, const T* rhs, i64 bs, T* out, i64 os, int nrhs,
+                                                         int right, i64 batch) {
+  for (i64 b0 = i64(blockIdx.x) * blockDim.x; b0 < batch; b0 += i64(gridDim.x) * blockDim.x) {
+    const bool valid = b0 + threadIdx.x < batch;
+    const i64 b = valid ? b0 + threadIdx.x : batch - 1;
+    const T* src = mat + b * as;
+    T a[N][N];
+    int piv[N];
+    static_for<0, N>([&](auto I) {
+      static_for<0, N>([&](auto J) {
+        constexpr int i = I, j = J;
+        if constexpr (CHOL) a[i][j] = src[(i > j ? i : j) * N + (i > j ? j : i)];  // lower triangle, symmetric
+        else a[i][j] = right ? src[j * N + i] : src[i * N + j];
+      });
+    });
+    if constexpr (!CHOL) {
+      static_for<0, N>([&](auto K) {
+        constexpr int k = K;
+        T best = tabs(a[k][k]);
+        int p = k;
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const T c = tabs(a[i][k]);
+          if (c > best) {
+            best = c;
+            p = i;
+          }
+        });
+        piv[k] = p;
+        if (warp_any(p != k)) {
+          static_for<k + 1, N>([&](auto I) {
+            constexpr int i = I;
+            const bool sw = (p == i);
+            static_for<0, N>([&](auto J) {
+              constexpr int j = J;
+              const T lo = a[k][j], hi = a[i][j];
+              a[k][j] = sw ? hi : lo;
+              a[i][j] = sw ? lo : hi;
+            });
+          });
+        }
+        const T rp = T(1) / a[k][k];
+        a[k][k] = rp;  // the reciprocal pivot is what the substitutions need
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const T f = a[i][k] * rp;
+          a[i][k] = f;
+          static_for<k + 1, N>([&](auto J) {
+            constexpr int j = J;
+            a[i][j] -= f * a[k][j];
+          });
+        });
+      });
+    } else {
+      // LDL^T: strictly-lower part holds L, diagonal holds 1 / d
+      static_for<0, N>([&](auto K) {
+        constexpr int k = K;
+        const T rp = T(1) / a[k][k];
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          static_for<k + 1, i + 1>([&](auto J) {
+            constexpr int j = J;
+            a[i][j] -= a[i][k] * a[j][k] * rp;
+          });
+        });
+        static_for<k + 1, N>([&](auto I) { a[I][k] *= rp; });
+        a[k][k] = rp;
+        piv[k] = k;
+      });
+    }
+    const T* bb = rhs + b * bs;
+    T* xx = out + b * os;
+    for (int c = 0; c < nrhs; ++c) {
+      T x[N];
+      static_for<0, N>([&](auto I) { x[I] = right ? bb[c * N + I] : bb[I * nrhs + c]; });
+      if constexpr (!CHOL) {
+        // the factorisation exchanged whole rows (multipliers included, as LAPACK's getrf), so
+        // all exchanges are applied to the right-hand side first, then L y = P b
+        static_for<0, N>([&](auto K) {
+          constexpr int k = K;
+          if (warp_any(piv[k] != k)) {
+            static_for<k + 1, N>([&](auto I) {
+              constexpr int i = I;
+              const bool sw = (piv[k] == i);
+              const T lo = x[k], hi = x[i];
+              x[k] = sw ? hi : lo;
+              x[i] = sw ? lo : hi;
+            });
+          }
+        });
+        static_for<0, N>([&](auto K) {
+          constexpr int k = K;
+          static_for<k + 1, N>([&](auto I) { x[I] -= a[I][k] * x[k]; });
+        });
+        static_for_down<0, N>([&](auto K) {  // U x = y
+          constexpr int k = K;
+          T sum = x[k];
+          static_for<k + 1, N>([&](auto J) { sum -= a[k][J] * x[J]; });
+          x[k] = sum * a[k][k];
+        });
+      } else {
+        static_for<0, N>([&](auto K) { static_for<K + 1, N>([&](auto I) { x[I] -= a[I][K] * x[K]; }); });
+        static_for<0, N>([&](auto K) { x[K] *= a[K][K]; });
+        static_for_down<0, N>([&](auto K) { static_for<K + 1, N>([&](auto J) { x[K] -= a[J][K] * x[J]; }); });
+      }
+      if (valid) static_for<0, N>([&](auto I) { (right ? xx[c * N + I] : xx[I * nrhs + c]) = x[I]; });
+    }
+  }
+}
+
 // J^T H J (mode 0) or J H J^T (mode 1, k == d) for any 1 <= k, d <= 10:
 // run-time-sized fallback of the templated SymMatmulOp (k, d <= 4)
 template <typename T>
@@ -157,6 +280,29 @@ int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, 
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }
+
+template <typename T, int N>
+static int solve_many_n(int n, int nrhs, int chol, int right, i64 batch, const T* a, i64 as, const T* b, i64 bs, T* out, i64 os,
+                        cudaStream_t s) {
+  if (n == N) {
+    if (chol) solve_many_kernel<T, N, true><<<grid_for(batch), 128, 0, s>>>(a, as, b, bs, out, os, nrhs, right, batch);
+    else solve_many_kernel<T, N, false><<<grid_for(batch), 128, 0, s>>>(a, as, b, bs, out, os, nrhs, right, batch);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return int(cudaGetLastError());
+  }
+  if constexpr (N < NFM_MAX_N) return solve_many_n<T, N + 1>(n, nrhs, chol, right, batch, a, as, b, bs, out, os, s);
+  else return NFM_E_UNSUPPORTED;
+}
+
+template <typename T>
+int batch_solve_many(int n, int nrhs, int chol, int right, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out,
+                     i64 os, cudaStream_t s) {
+  if (batch == 0) return 0;
+  return solve_many_n<T, 1>(n, nrhs, chol, right, batch, static_cast<const T*>(a), as, static_cast<const T*>(b), bs,
+                            static_cast<T*>(out), os, s);
+}
+template int batch_solve_many<float>(int, int, int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
+template int batch_solve_many<double>(int, int, int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
 
 template int batch_matvec_rt<float>(int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
 template int batch_matvec_rt<double>(int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);

@@ -54,6 +54,12 @@ template <typename T> int sym_matmul_impl(int k, int d, int mode, const KParams&
 template <typename T> int sym_matmul_solve_impl(int k, int d, int mode, const KParams& p, cudaStream_t s);
 template <typename T> int sym_solve_update_impl(int n, int algo, const KParams& p, cudaStream_t s);
 
+// nrhs > 4 and right division: register factorisation (order templated), run-time loop over
+// the right-hand sides (nfm_generic.cu)
+template <typename T>
+int batch_solve_many(int n, int nrhs, int chol, int right, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out,
+                     i64 os, cudaStream_t s);
+
 template <typename T>
 int sym_matmul_rt(int k, int d, int mode, i64 batch, const void* jac, i64 js, const void* hess, i64 hs, void* out, i64 os,
                   cudaStream_t s);

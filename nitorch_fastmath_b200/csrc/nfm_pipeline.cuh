@@ -1,16 +1,18 @@
-// nfm_pipeline.cuh -- the two kernels every op runs through.
+// nfm_pipeline.cuh -- the kernels every op runs through.
 //
-//   tile_kernel<Op, THREADS, MPT, STAGES, SEG>  (fast path)
+//   tile_kernel<Op, THREADS, MPT, STAGES, SEG>  (fast path, light ops)
 //     Persistent CTAs, one thread per matrix (MPT matrices per thread per
 //     tile).  The AoS records (coefficient dimension last) of a tile of
-//     TILE = THREADS*MPT consecutive matrices are one contiguous byte range
-//     per operand, so each operand tile moves HBM -> shared memory with 1-D
-//     TMA bulk copies (cp.async.bulk, completion on an mbarrier) into a
-//     STAGES-deep ring; threads pull their own record out of shared memory
-//     with the widest conflict-free access, compute in registers, stage the
-//     result record in shared memory and the tile goes back with TMA bulk
-//     stores.  Every HBM access is therefore a full, aligned, contiguous
-//     burst regardless of the record length.
+//     consecutive matrices are one contiguous byte range per operand, so each
+//     operand tile moves HBM -> shared memory with 1-D TMA bulk copies
+//     (cp.async.bulk, completion on an mbarrier) into a STAGES-deep ring;
+//     threads pull their own record out of shared memory with the widest
+//     conflict-free access, compute in registers, stage the result record in
+//     shared memory and the tile goes back with TMA bulk stores.  Every HBM
+//     access is therefore a full, aligned, contiguous burst regardless of the
+//     record length.  The number of matrices per tile is a run-time argument
+//     (full tiles + one partial tile, both by TMA); the first tiles are
+//     prefetched into L2 ahead of the programmatic-dependent-launch wait.
 //
 //     SEG = false: one bulk copy per operand per tile, record r of the tile at
 //       r * record_bytes.  Conflict free whenever record_bytes is an odd
@@ -23,10 +25,14 @@
 //       128-bit shared-memory phase then sit in 8 different segments, i.e. 8
 //       different 16 B bank groups: conflict free for every record size.
 //
+//   pool_kernel<Op, MAXW, MPT, SEG>  (fast path, pivoted ops on large records)
+//     One persistent CTA per SM owns a pool of TMA buffers of one warp-tile
+//     each; its warps run independently, results are written in place.
+//
 //   strided_kernel<Op>  (general path)
 //     One thread per matrix straight from global memory with arbitrary batch
-//     strides / alignment / broadcast.  Also runs the ragged tail
-//     (batch % TILE) of the fast path.
+//     strides / alignment / broadcast.  Also runs the < 4-matrix head / tail
+//     that cannot keep the 16-byte granularity of bulk copies.
 //
 // An Op is a stateless struct:
 //     using scalar = float|double;
@@ -34,8 +40,8 @@
 //     [static constexpr int kLen3;]               // optional fourth input (bit 8 of kUse)
 //     static constexpr int kUse;                   // bit mask of inputs the op can take
 //     static constexpr int kOut;                   // output record length
-//     static constexpr bool kHeavy;                // pivoted / long dependent chains (tile geometry hint)
-//     __device__ static void apply(const T(&)[kLen0], const T(&)[kLen1], const T(&)[kLen2],
+//     static constexpr bool kHeavy;                // pivoted / long dependent chains (kernel + geometry choice)
+//     __device__ static void apply(const T(&)[kLen0], const T(&)[kLen1], const T(&)[kLen2], [const T(&)[kLen3],]
 //                                  int present, int flags, T(&out)[kOut]);
 // Absent optional inputs arrive zero-filled.
 #pragma once
@@ -934,7 +940,6 @@ int launch_strided(const KParams& p, cudaStream_t stream) {
 template <class Op>
 int run_op(KParams p, cudaStream_t stream) {
   using Tn = Tune<Op>;
-  constexpr int TILE = Tn::kThreads * Tn::kMpt;
   t_last_path_tma = 0;
   if (p.batch == 0) return NFM_OK;
   const int lens[kMaxIn] = {Op::kLen0, Op::kLen1, Op::kLen2, len3<Op>::value};
@@ -985,23 +990,20 @@ int run_op(KParams p, cudaStream_t stream) {
     }
   }
   if (fast) {
-    // full tiles by TMA, the ragged remainder inside the same launch
+    // full tiles and the partial tile by TMA; the < 4-matrix tail in a second tiny launch
     int rc;
     if constexpr (PoolTune<Op>::kEnabled) {
       using Pt = PoolTune<Op>;
       int warps, nbuf;
       Pt::geometry(PoolGeom<Op, Pt::kMpt, Tn::kSeg>::buf_bytes(staged_mask(p)), device_info().max_smem_optin, warps, nbuf);
       rc = launch_pool<Op, Pt::kMaxW, Pt::kMpt, Tn::kSeg>(p, warps, nbuf, stream);
-    } else {
-    bool small = false;
-    if constexpr (TuneSmall<Op>::kEnabled) small = p.batch * TuneSmall<Op>::kRec < TuneSmall<Op>::kBelowBytes;
-    if constexpr (TuneSmall<Op>::kEnabled) {
+    } else if constexpr (TuneSmall<Op>::kEnabled) {
       using Ts = TuneSmall<Op>;
+      const bool small = p.batch * Ts::kRec < Ts::kBelowBytes;
       rc = small ? launch_tile<Op, Ts::kThreads, Ts::kMpt, Ts::kStages, Tn::kSeg>(p, stream)
                  : launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, stream);
     } else {
       rc = launch_tile<Op, Tn::kThreads, Tn::kMpt, Tn::kStages, Tn::kSeg>(p, stream);
-    }
     }
     if (rc == 0) {
       t_last_path_tma = PoolTune<Op>::kEnabled ? 3 : 1;

@@ -84,14 +84,44 @@ def lmdiv(a: Tensor, b: Tensor, method: str = 'lu', rcond: float = 1e-15, out: O
 
 
 def rmdiv(a: Tensor, b: Tensor, method: str = 'lu', rcond: float = 1e-15, out: Optional[Tensor] = None) -> Tensor:
-    r"""Right matrix division ``a @ inv(b)``  (reference sugar.py:140-191):
-    solved as ``(inv(b^T) @ a^T)^T``."""
-    r = lmdiv(torch.as_tensor(b).transpose(-1, -2), torch.as_tensor(a).transpose(-1, -2), method=method)
-    r = r.transpose(-1, -2)
-    if out is not None:
-        out.copy_(r)
-        return out
-    return r
+    r"""Right matrix division ``a @ inv(b)``  (reference sugar.py:140-191, its documented meaning;
+    as written the reference returns ``lmdiv(b, a)^T = (inv(b) @ a)^T`` and only runs for square ``a``).
+
+    a : `(..., k, n)`, b : `(..., n, n)` -> `(..., k, n)`.  Solved natively as ``b^T x_r = a_r`` for every
+    row ``r`` (``nfm_batch_rsolve``): neither operand is transposed or copied.
+    """
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    if b.shape[-1] != b.shape[-2]:
+        raise NotImplementedError("non-square systems (pseudo-inverse) are outside the B200 hot path")
+    algo = _algo(method)
+    dev = D.common_device(a, b)
+    if dev.type != "cuda":
+        cuda = _host.offload_device()
+        r = rmdiv(a.to(cuda), b.to(cuda), method=method).cpu()
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+    n = b.shape[-1]
+    if not 1 <= n <= _lib.MAX_N:
+        raise ValueError(f"matrix order {n} is outside the supported range 1..{_lib.MAX_N}")
+    if a.shape[-1] != n:
+        raise ValueError("a and b have incompatible shapes")
+    k = a.shape[-2]
+    cdt = D.compute_dtype(a, b)
+    batch = tuple(torch.broadcast_shapes(a.shape[:-2], b.shape[:-2]))
+    nb = D.batch_count(batch)
+    o, res, copy_back = D.out_operand(out, (*batch, k, n), 2, cdt, dev)
+    if nb > 0 and k > 0:
+        ao = D.as_operand(a, batch, 2, cdt)
+        bo = D.as_operand(b, batch, 2, cdt)
+        with D.device_of(dev):
+            rc = _lib.load().nfm_batch_rsolve(D.dtype_code(cdt), n, k, algo, nb, bo.ptr, bo.stride, ao.ptr, ao.stride,
+                                              o.ptr, o.stride, D.current_stream_ptr(dev))
+        _lib.check(rc, "nfm_batch_rsolve")
+    if copy_back:
+        res.copy_(o.tensor)
+    return res
 
 
 def inv(a: Tensor, method: str = 'lu', rcond: float = 1e-15, out: Optional[Tensor] = None) -> Tensor:

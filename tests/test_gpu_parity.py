@@ -1036,3 +1036,30 @@ def test_storage_offset_views_take_the_tma_path(nfm, n):
     assert torch.equal(x, nfm.sym_solve(mat[1:].clone(), vec[1:].clone()))
     inv = nfm.sym_invert(mat[1:])
     close(inv, P.sym_invert(mat[1:].cpu()), dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 3, 6, 10])
+def test_many_right_hand_sides_and_right_division(nfm, dtype, n):
+    """lmdiv with more than 4 right-hand sides and rmdiv run on the register-factorisation
+    kernel (order templated, run-time loop over the right-hand sides); rmdiv solves
+    b^T x_r = a_r natively -- no transposed copies."""
+    batch = 5003
+    a = _row_permuted(G.dense_shifted(batch, n, dtype, seed=n), seed=n)          # half of the lanes pivot
+    spd = G.dense_spd(batch, n, dtype, seed=n + 1)
+    for k in (5, 7, 12):
+        b = G.vectors((batch, n), k, dtype, seed=k)
+        close(nfm.lmdiv(a.to(DEV), b.to(DEV)), P.lmdiv(a, b), dtype, 2, scale=4)
+        close(nfm.lmdiv(spd.to(DEV), b.to(DEV), "chol"), P.lmdiv(spd, b, "chol"), dtype, 2, scale=4)
+    for k in (1, 3, 4, 9):
+        r = G.vectors((batch, k), n, dtype, seed=20 + k)                          # (batch, k, n)
+        want = (r.double() @ torch.linalg.inv(a.double())).to(dtype)              # the documented a @ inv(b)
+        got = nfm.rmdiv(r.to(DEV), a.to(DEV))
+        close(got, want, dtype, 2, scale=4)
+        want_c = (r.double() @ torch.linalg.inv(spd.double())).to(dtype)
+        close(nfm.rmdiv(r.to(DEV), spd.to(DEV), "chol"), want_c, dtype, 2, scale=4)
+        out = torch.empty(batch, k, n, device=DEV, dtype=dtype)
+        assert nfm.rmdiv(r.to(DEV), a.to(DEV), out=out) is out and torch.equal(out, got)
+    # broadcasting: one system for the whole batch
+    r = G.vectors((batch, 2), n, dtype, seed=77)
+    close(nfm.rmdiv(r.to(DEV), a[0].to(DEV)), (r.double() @ torch.linalg.inv(a[0].double())).to(dtype), dtype, 2, scale=4)
