@@ -184,7 +184,7 @@ struct BatchMatvecOp {
 // measured optima (profiles/r1_tile_geometry_sweep.txt): fp64 pivoted elimination
 // wants more resident warps than the one-big-CTA rule gives
 template <> struct Tune<BatchInvOp<double, 4, NFM_ALGO_AUTO>> : TuneFixed<BatchInvOp<double, 4, NFM_ALGO_AUTO>, 256, 256, 3> {};
-template <> struct Tune<BatchDetOp<double, 4>> : TuneFixed<BatchDetOp<double, 4>, 256, 256, 3> {};  // round 2: 342 vs 350 us (128 x 2)
+template <> struct Tune<BatchDetOp<double, 4>> : TuneFixed<BatchDetOp<double, 4>, 256, 128, 3> {};
 template <> struct Tune<BatchSolveOp<double, 4, NFM_ALGO_LU>> : TuneFixed<BatchSolveOp<double, 4, NFM_ALGO_LU>, 128, 128, 3> {};
 // fp32 4x4 (sweep 3): 6073 vs 5850 GB/s (solve), 6378 vs 5930 GB/s (det)
 template <> struct Tune<BatchSolveOp<float, 4, NFM_ALGO_LU>> : TuneFixed<BatchSolveOp<float, 4, NFM_ALGO_LU>, 256, 256, 3> {};

@@ -249,7 +249,11 @@ __global__ void __launch_bounds__(THREADS)
   const T* const g3 = static_cast<const T*>(p.in[3].ptr);
   T* const gout = static_cast<T*>(p.out);
   // matrices in tile t
+#ifdef NFM_AB_STATICTILE
+  auto count_of = [&](i64) { return G::kTile; };
+#else
   auto count_of = [&](i64 t) { return t < ntiles ? tile_m : part_m; };
+#endif
 
   uint64_t policy = 0;
   if (tid == 0) {
@@ -284,11 +288,14 @@ __global__ void __launch_bounds__(THREADS)
   NFM_STAMP(1);
 
   // producer (threads 0..kIssuers-1): thread 0 arms the stage barrier with the
-  // tile's byte count; each issuer sends its segment of every staged operand
-  auto issue = [&](int stage, i64 tile) {
+  // tile's byte count; each issuer sends its segment of every staged operand.
+  // `per_seg_c` (matrices per segment; per tile when !SEG) is a compile-time constant for
+  // full-capacity tiles and a run-time value for the others: with run-time byte counts on
+  // every copy the segmented 4x4 fp64 kernels lost 4 % (profiles/r2_kernel_ab.txt).
+  auto issue_n = [&](int stage, i64 tile, auto per_seg_c) {
     unsigned char* dst = in_base + stage * stage_bytes;
     const i64 first = tile * tile_m;
-    const int per_seg = count_of(tile) / nseg;  // matrices per segment (per tile when !SEG)
+    const int per_seg = per_seg_c;
     if (tid == 0) mbar_arrive_expect_tx(&full[stage], uint32_t(per_seg * nseg * staged_len * es));
     const int seg = SEG ? tid : 0;  // segment `seg` lands at its fixed (capacity) offset
     if (staged & 1) {
@@ -313,6 +320,12 @@ __global__ void __launch_bounds__(THREADS)
                         sb, &full[stage], policy);
       }
     }
+  };
+  // tiles below `nstatic` hold exactly the capacity (always, unless equal-tile scheduling cut them)
+  const i64 nstatic = tile_m == G::kTile ? ntiles : 0;
+  auto issue = [&](int stage, i64 tile) {
+    if (tile < nstatic) issue_n(stage, tile, std::integral_constant<int, G::kTile / nseg>{});
+    else issue_n(stage, tile, count_of(tile) / nseg);
   };
 
   if (tid < kIssuers) {
@@ -381,9 +394,15 @@ __global__ void __launch_bounds__(THREADS)
     __syncthreads();
     if (tid < kIssuers) {
       const int seg = SEG ? tid : 0;
-      const int sbo = (cnt / nseg) * Op::kOut * es;
-      bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * tile_m * Op::kOut) + seg * sbo, sout + seg * G::seg_stride(Op::kOut),
-               sbo);
+      if (tile < nstatic) {
+        constexpr int sbo = (G::kTile / nseg) * Op::kOut * es;
+        bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * i64(G::kTile) * Op::kOut) + seg * sbo,
+                 sout + seg * G::seg_stride(Op::kOut), sbo);
+      } else {
+        const int sbo = (cnt / nseg) * Op::kOut * es;
+        bulk_s2g(reinterpret_cast<unsigned char*>(gout + tile * tile_m * Op::kOut) + seg * sbo, sout + seg * G::seg_stride(Op::kOut),
+                 sbo);
+      }
       bulk_commit();
     }
   }
