@@ -254,7 +254,7 @@ class ClockSampler:
         0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period: float = 0.0005):
+    def __init__(self, index: int, period: float = 0.002):
         import subprocess
         import tempfile
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -532,6 +532,23 @@ def run_workload(args, rank, local_rank, world, dist):
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel": "%s<%s n=%d %s> (%d launch(es) per step per GPU, TMA-staged)" % (kernel, kind, n, w["dtype"], launches // max(args.steps, 1)),
                 "bytes_per_launch": my * alg, "avg_launch_us": local_ms * 1e3}
+
+    # small working sets: the same K steps on ONE operand set, i.e. with the data resident in the
+    # 126 MB L2 -- reported next to the HBM figure above (rotated sets), never instead of it
+    if nsets > 1:
+        one = [launchers[0]] * args.steps
+        for f in one[:3]:
+            f()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f in one:
+            f()
+        e1.record()
+        sync()
+        l2_ms = e0.elapsed_time(e1) / args.steps
+        roofline["l2_resident"] = {"avg_launch_us": l2_ms * 1e3, "achieved": my * alg / (l2_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                   "note": "same launches on one operand set (%.0f MiB, stays in L2): NOT an HBM figure" % (set_bytes / 2**20)}
 
     # end to end: host (pinned) operands through the public API
     e2e = None

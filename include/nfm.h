@@ -193,7 +193,7 @@ int nfm_sym_outer(int dtype, int n, int64_t batch,
  * and what its general branch jhjn computes (:596-634).
  * mode 1: out = J H J^T  (k == d) -- what the reference's unrolled branches
  * jhj1/2/3 compute for k == d <= 3 (:532-593).  1 <= k, d <= 10 (register
- * kernels up to 6 x 6, a run-time-sized kernel above).
+ * kernels for k, d <= 6 and for k <= 10 with d <= 3; a run-time-sized kernel otherwise).
  * Replaces sym_matmul _impl/sym.py:637-670. */
 int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch,
                    const void *jac, int64_t jac_stride,
@@ -205,7 +205,8 @@ int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch,
  *     out = (J^T H J + diag(d))^-1 g          (mode 0)
  *     out = (J H J^T + diag(d))^-1 g          (mode 1, k == d <= 3: the reference's unrolled branches)
  * jac: k x d row-major, hess: packed k(k+1)/2 (mode 0), grad / diag / out: records of d
- * (mode 0); diag may be NULL.  1 <= k, d <= 6.
+ * (mode 0); diag may be NULL.  1 <= k, d <= 6, or k <= 10 with d <= 3 (many channels,
+ * a 1..3-parameter step).
  * Replaces the chain sym_matmul -> sym_solve, _impl/sym.py:637-670 then :327-398. */
 int nfm_sym_matmul_solve(int dtype, int k, int d, int mode, int64_t batch,
                          const void *jac, int64_t jac_stride,

@@ -103,7 +103,7 @@ int nfm_sym_matmul(int dtype, int k, int d, int mode, int64_t batch, const void*
   }
   if (batch < 0 || !jac || !hess || !out || jac_stride < 0 || hess_stride < 0 || out_stride < 0) { set_error("bad argument"); return NFM_E_BADARG; }
   auto st = static_cast<cudaStream_t>(stream);
-  if (k > kFusedMaxOrder || d > kFusedMaxOrder || (mode == 1 && k > 3)) {  // run-time-sized kernel above the templated 6 x 6
+  if (!fused_shape_built(k, d) || (mode == 1 && k > 3)) {  // run-time-sized kernel beyond the templated shapes
     const int rc = dtype == NFM_F32 ? sym_matmul_rt<float>(k, d, mode, batch, jac, jac_stride, hess, hess_stride, out, out_stride, st)
                                     : sym_matmul_rt<double>(k, d, mode, batch, jac, jac_stride, hess, hess_stride, out, out_stride, st);
     if (rc) set_error("sym_matmul kernel launch failed: %s", cudaGetErrorString(cudaError_t(rc)));
@@ -125,8 +125,8 @@ int nfm_sym_matmul_solve(int dtype, int k, int d, int mode, int64_t batch, const
                          int64_t hess_stride, const void* grad, int64_t grad_stride, const void* diag, int64_t diag_stride,
                          void* out, int64_t out_stride, void* stream) {
   if (dtype != NFM_F32 && dtype != NFM_F64) { set_error("dtype must be NFM_F32 or NFM_F64"); return NFM_E_UNSUPPORTED; }
-  if (k < 1 || k > kFusedMaxOrder || d < 1 || d > kFusedMaxOrder || (mode != 0 && mode != 1) || (mode == 1 && (k != d || k > 3))) {
-    set_error("sym_matmul_solve: 1 <= k, d <= 6; mode 1 needs k == d <= 3");
+  if (!fused_shape_built(k, d) || (mode != 0 && mode != 1) || (mode == 1 && (k != d || k > 3))) {
+    set_error("sym_matmul_solve: 1 <= k, d <= 6, or k <= 10 with d <= 3; mode 1 needs k == d <= 3");
     return NFM_E_UNSUPPORTED;
   }
   if (batch < 0 || !jac || !hess || !grad || !out || jac_stride < 0 || hess_stride < 0 || grad_stride < 0 || diag_stride < 0 ||

@@ -1,6 +1,6 @@
 // nfm_fused.cu -- the Gauss-Newton neighbours of the solve,
 // compiled once per scalar type (-DNFM_SCALAR) and part (-DNFM_PART):
-//   part 0: sym_matmul          J^T H J -> packed           (register kernels up to 6 x 6)
+//   part 0: sym_matmul          J^T H J -> packed           (register kernels for k, d <= 6 and for k <= 10, d <= 3)
 //   part 1: sym_matmul_solve    (J^T H J + diag(d))^-1 g    fused: the packed Hessian stays in registers
 //   part 2: sym_solve_update    x - alpha (A + lam I + diag(d))^-1 v
 #include "nfm_impl.cuh"
@@ -55,6 +55,17 @@ static int fused_d(int d, int mode, const KParams& p, cudaStream_t s) {
   return NFM_E_UNSUPPORTED;
 }
 
+// tall Jacobians (many channels / features, a 1..3-parameter displacement): k = 7..10, d <= 3
+template <typename T, int K>
+static int fused_d_tall(int d, int mode, const KParams& p, cudaStream_t s) {
+  switch (d) {
+    case 1: return NFM_FUSED_RUN<T, K, 1>(mode, p, s);
+    case 2: return NFM_FUSED_RUN<T, K, 2>(mode, p, s);
+    case 3: return NFM_FUSED_RUN<T, K, 3>(mode, p, s);
+  }
+  return NFM_E_UNSUPPORTED;
+}
+
 template <typename T>
 static int fused_kd(int k, int d, int mode, const KParams& p, cudaStream_t s) {
   switch (k) {
@@ -64,6 +75,10 @@ static int fused_kd(int k, int d, int mode, const KParams& p, cudaStream_t s) {
     case 4: return fused_d<T, 4>(d, mode, p, s);
     case 5: return fused_d<T, 5>(d, mode, p, s);
     case 6: return fused_d<T, 6>(d, mode, p, s);
+    case 7: return fused_d_tall<T, 7>(d, mode, p, s);
+    case 8: return fused_d_tall<T, 8>(d, mode, p, s);
+    case 9: return fused_d_tall<T, 9>(d, mode, p, s);
+    case 10: return fused_d_tall<T, 10>(d, mode, p, s);
   }
   return NFM_E_UNSUPPORTED;
 }

@@ -48,8 +48,11 @@ template <typename T>
 int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out, i64 os,
                    cudaStream_t s);
 
-// nfm_fused.cu: register kernels for 1 <= k, d <= 6 (kFusedMaxOrder)
+// nfm_fused.cu: register kernels for 1 <= k, d <= 6 and for tall Jacobians k <= 10, d <= 3
 constexpr int kFusedMaxOrder = 6;
+inline bool fused_shape_built(int k, int d) {
+  return k >= 1 && d >= 1 && ((k <= kFusedMaxOrder && d <= kFusedMaxOrder) || (k <= NFM_MAX_N && d <= 3));
+}
 template <typename T> int sym_matmul_impl(int k, int d, int mode, const KParams& p, cudaStream_t s);
 template <typename T> int sym_matmul_solve_impl(int k, int d, int mode, const KParams& p, cudaStream_t s);
 template <typename T> int sym_solve_update_impl(int n, int algo, const KParams& p, cudaStream_t s);

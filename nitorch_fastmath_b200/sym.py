@@ -431,7 +431,7 @@ def sym_matmul_solve(j: Tensor, h: Tensor, g: Tensor, diag=None, out: Optional[T
     (reference _impl/sym.py:637-670 then :327-398): the ``d*(d+1)//2``-coefficient Hessian
     field is never written to memory.  ``j (..., k, d)``, ``h (..., k*(k+1)//2)`` or
     diagonal ``(..., k)``, ``g (..., d)``, ``diag`` float / sequence / ``(..., d)``;
-    ``1 <= k, d <= 6``; CUDA tensors.  Like ``sym_matmul`` it evaluates ``J H J^T``
+    ``1 <= k, d <= 6`` or ``k <= 10`` with ``d <= 3``; CUDA tensors.  Like ``sym_matmul`` it evaluates ``J H J^T``
     for ``k == d <= 3`` (the reference's unrolled branches).  Not a function of the reference.
     """
     j, h, g = torch.as_tensor(j), torch.as_tensor(h), torch.as_tensor(g)
@@ -439,8 +439,8 @@ def sym_matmul_solve(j: Tensor, h: Tensor, g: Tensor, diag=None, out: Optional[T
     if dev.type != "cuda":
         raise RuntimeError("sym_matmul_solve takes CUDA tensors")
     k, d = j.shape[-2:]
-    if not (1 <= k <= 6 and 1 <= d <= 6):
-        raise ValueError("sym_matmul_solve supports 1 <= k, d <= 6 (use sym_matmul + sym_solve above)")
+    if not ((1 <= k <= 6 and 1 <= d <= 6) or (1 <= k <= _lib.MAX_N and 1 <= d <= 3)):
+        raise ValueError("sym_matmul_solve supports 1 <= k, d <= 6, or k <= 10 with d <= 3 (use sym_matmul + sym_solve otherwise)")
     if h.shape[-1] == k and k > 1:
         h = torch.cat([h, h.new_zeros((*h.shape[:-1], k * (k - 1) // 2))], -1)
     if h.shape[-1] != k * (k + 1) // 2:

@@ -968,7 +968,7 @@ def test_fused_matmul_solve(nfm, dtype):
     sym_matmul -> sym_solve (reference _impl/sym.py:637-670 then :327-398), including
     the reference's J H J^T for k == d <= 3."""
     batch = 20_011
-    for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (6, 6), (2, 3), (3, 2), (4, 3), (6, 3), (3, 6), (5, 6), (6, 5)]:
+    for k, d in [(1, 1), (2, 2), (3, 3), (4, 4), (6, 6), (2, 3), (3, 2), (4, 3), (6, 3), (3, 6), (5, 6), (6, 5), (8, 3), (10, 3), (10, 2), (7, 1)]:
         j = G.vectors((batch, k), d, dtype, seed=k * 10 + d)
         j = 0.3 * j + 2 * torch.eye(k, d, dtype=dtype)    # singular values in about [1, 3]: J^T H J well conditioned when k >= d
         h = G.spd_packed(batch, k, dtype, seed=k)

@@ -27,7 +27,7 @@ def timeit(f, reps=20):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
-for k, d, B in ((3, 3, 1 << 24), (6, 6, 1 << 22), (6, 3, 1 << 23), (4, 4, 1 << 23)):
+for k, d, B in ((3, 3, 1 << 24), (6, 6, 1 << 22), (6, 3, 1 << 23), (4, 4, 1 << 23), (10, 3, 1 << 22)):
     j = torch.randn(B, k, d, device=dev) * 0.3 + 2 * torch.eye(k, d, device=dev)
     h = torch.rand(B, k * (k + 1) // 2, device=dev) * 0.1
     h[:, :k] += 4
