@@ -1,8 +1,9 @@
-// nfm_generic.cu -- run-time-sized kernels for the shapes the templated
-// register kernels do not cover: rectangular m x n matvec (batchmatvec's
-// "other sizes" branch, _impl/batched.py:175-176) and solves with several
-// right-hand sides (sugar.lmdiv, sugar.py:75-137).  Correct for any stride;
-// not on the measured hot path.
+// nfm_generic.cu -- kernels for the shapes the TMA-staged register kernels do not
+// cover: rectangular m x n matvec (batchmatvec's "other sizes" branch,
+// _impl/batched.py:175-176), solves with more than 4 right-hand sides and right
+// division (sugar.lmdiv / rmdiv, sugar.py:75-191; factorisation in registers, run-time
+// loop over the right-hand sides), and J^T H J beyond the templated shapes.  Correct for
+// any batch stride; not on the measured hot path.
 #include "nfm_pipeline.cuh"
 #include "nfm_sym_math.cuh"
 
@@ -20,68 +21,6 @@ __global__ void __launch_bounds__(128) matvec_rt_kernel(const T* __restrict__ ma
     T s = a[0] * v[0];
     for (int j = 1; j < n; ++j) s += a[j] * v[j];
     out[b * os + i] = s;
-  }
-}
-
-// LU with partial pivoting (LDL^T when chol) in local memory, then nrhs substitutions
-template <typename T>
-__global__ void __launch_bounds__(128) solve_rt_kernel(const T* mat, i64 as, const T* rhs, i64 bs, T* out, i64 os, int n,
-                                                       int nrhs, int chol, i64 batch) {
-  for (i64 b = i64(blockIdx.x) * blockDim.x + threadIdx.x; b < batch; b += i64(gridDim.x) * blockDim.x) {
-    T a[NFM_MAX_N][NFM_MAX_N];
-    int perm[NFM_MAX_N];
-    const T* src = mat + b * as;
-    for (int i = 0; i < n; ++i) {
-      perm[i] = i;
-      for (int j = 0; j < n; ++j) a[i][j] = chol ? src[(i > j ? i : j) * n + (i > j ? j : i)] : src[i * n + j];
-    }
-    if (!chol) {
-      for (int k = 0; k < n; ++k) {
-        int p = k;
-        T best = tabs(a[k][k]);
-        for (int i = k + 1; i < n; ++i) {
-          const T c = tabs(a[i][k]);
-          if (c > best) { best = c; p = i; }
-        }
-        if (p != k) {
-          for (int j = 0; j < n; ++j) { const T t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
-          const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
-        }
-        const T rp = T(1) / a[k][k];
-        for (int i = k + 1; i < n; ++i) {
-          const T f = a[i][k] * rp;
-          a[i][k] = f;
-          for (int j = k + 1; j < n; ++j) a[i][j] -= f * a[k][j];
-        }
-      }
-    } else {
-      // LDL^T: strictly-lower part holds L, diagonal holds D
-      for (int k = 0; k < n; ++k) {
-        const T rp = T(1) / a[k][k];
-        for (int i = k + 1; i < n; ++i)
-          for (int j = k + 1; j <= i; ++j) a[i][j] -= a[i][k] * a[j][k] * rp;
-        for (int i = k + 1; i < n; ++i) a[i][k] *= rp;
-      }
-    }
-    const T* bb = rhs + b * bs;
-    T* xx = out + b * os;
-    for (int c = 0; c < nrhs; ++c) {
-      T x[NFM_MAX_N];
-      for (int i = 0; i < n; ++i) x[i] = bb[perm[i] * nrhs + c];
-      for (int i = 0; i < n; ++i)  // L y = P b
-        for (int j = 0; j < i; ++j) x[i] -= a[i][j] * x[j];
-      if (chol) {
-        for (int i = 0; i < n; ++i) x[i] /= a[i][i];
-        for (int i = n - 1; i >= 0; --i)
-          for (int j = i + 1; j < n; ++j) x[i] -= a[j][i] * x[j];
-      } else {
-        for (int i = n - 1; i >= 0; --i) {
-          for (int j = i + 1; j < n; ++j) x[i] -= a[i][j] * x[j];
-          x[i] /= a[i][i];
-        }
-      }
-      for (int i = 0; i < n; ++i) xx[i * nrhs + c] = x[i];
-    }
   }
 }
 
@@ -271,16 +210,6 @@ int batch_matvec_rt(int m, int n, i64 batch, const void* mat, i64 ms, const void
   return int(cudaGetLastError());
 }
 
-template <typename T>
-int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out, i64 os,
-                   cudaStream_t s) {
-  if (batch == 0) return 0;
-  solve_rt_kernel<T><<<grid_for(batch), 128, 0, s>>>(static_cast<const T*>(a), as, static_cast<const T*>(b), bs,
-                                                     static_cast<T*>(out), os, n, nrhs, chol, batch);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  return int(cudaGetLastError());
-}
-
 template <typename T, int N>
 static int solve_many_n(int n, int nrhs, int chol, int right, i64 batch, const T* a, i64 as, const T* b, i64 bs, T* out, i64 os,
                         cudaStream_t s) {
@@ -306,7 +235,5 @@ template int batch_solve_many<double>(int, int, int, int, i64, const void*, i64,
 
 template int batch_matvec_rt<float>(int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
 template int batch_matvec_rt<double>(int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
-template int batch_solve_rt<float>(int, int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
-template int batch_solve_rt<double>(int, int, int, i64, const void*, i64, const void*, i64, void*, i64, cudaStream_t);
 
 }  // namespace nfm

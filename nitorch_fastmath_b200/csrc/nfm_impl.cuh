@@ -44,9 +44,6 @@ template <typename T> int batch_solvek_ldl_impl(int n, int k, const KParams& p, 
 template <typename T>
 int batch_matvec_rt(int m, int n, i64 batch, const void* mat, i64 ms, const void* vec, i64 vs, void* out, i64 os,
                     cudaStream_t s);
-template <typename T>
-int batch_solve_rt(int n, int nrhs, int chol, i64 batch, const void* a, i64 as, const void* b, i64 bs, void* out, i64 os,
-                   cudaStream_t s);
 
 // nfm_fused.cu: register kernels for 1 <= k, d <= 6 and for tall Jacobians k <= 10, d <= 3
 constexpr int kFusedMaxOrder = 6;
