@@ -133,3 +133,33 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.NfmError):
         _lib.load()
+
+
+def test_outer_split_finds_the_leading_dims_to_loop_over():
+    """Partially broadcast operands are not materialised: the Python layer loops over the
+    leading batch dims and launches on views (_dispatch.outer_split / outer_views)."""
+    import torch
+    from nitorch_fastmath_b200 import _dispatch as D
+    vec = torch.zeros(3, 4, 5, 3)
+    assert D.outer_split((3, 4, 5), [(torch.zeros(3, 4, 5, 6), 1), (vec, 1)]) == 0        # dense: nothing to split
+    assert D.outer_split((3, 4, 5), [(torch.zeros(6), 1), (vec, 1), (None, 1)]) == 0        # fully broadcast
+    assert D.outer_split((3, 4, 5), [(torch.zeros(1, 4, 5, 6), 1), (vec, 1)]) == 1          # one field for the batch
+    assert D.outer_split((3, 4, 5), [(torch.zeros(3, 1, 1, 6), 1), (vec, 1)]) == 1          # one matrix per image
+    assert D.outer_split((3, 4, 5), [(torch.zeros(3, 1, 5, 6), 1), (vec, 1)]) == 2          # broadcast in the middle
+    assert D.outer_split((3, 4, 5), [(torch.zeros(1, 4, 5, 6), 1), (vec, 1)], max_outer=2) == 0   # too many launches
+    v = D.outer_views(torch.arange(120.).view(1, 4, 5, 6), (3, 4, 5), 1, (2,))
+    assert v.shape == (4, 5, 6) and v.stride() == (30, 6, 1)          # a view of the one shared field, no copy
+    assert D.outer_views(None, (3, 4, 5), 1, (0,)) is None
+
+
+def test_empty_like_phased_matches_the_misalignment_of_its_reference():
+    import torch
+    from nitorch_fastmath_b200 import _dispatch as D
+    base = torch.zeros(1000 * 3 + 3)
+    for start in (0, 1, 2, 3):
+        ref = base[start:start + 999].view(333, 3)
+        out = D.empty_like_phased(ref)
+        assert out.shape == ref.shape and out.dtype == ref.dtype and out.is_contiguous()
+        assert out.data_ptr() % 16 == ref.data_ptr() % 16
+    out = D.empty_like_phased(base[1:7], shape=(2, 5))
+    assert out.shape == (2, 5) and out.data_ptr() % 16 == base[1:7].data_ptr() % 16
