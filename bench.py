@@ -384,6 +384,9 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="custom workload: matrix order")
     ap.add_argument("--dtype", default=None, choices=["f32", "f64"], help="custom workload: scalar type")
     ap.add_argument("--method", default="auto", choices=sorted(ALGOS), help="factorisation for sym_solve / sym_invert, N > 4")
+    ap.add_argument("--launch", default=os.environ.get("NFM_BENCH_LAUNCH", "graph"), choices=["graph", "eager"],
+                    help="how the K timed steps reach the GPU: 'graph' = the K C-ABI calls captured once in a CUDA graph and "
+                         "replayed inside the timed region (the host cannot stall a 16 us launch); 'eager' = K ctypes calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
@@ -475,7 +478,12 @@ def run_workload(args, rank, local_rank, world, dist):
     timing["l2"] = (f"per-GPU working set {set_bytes / 2**20:.0f} MiB > L2" if nsets == 1 else
                     f"rotating {nsets} operand sets of {set_bytes / 2**20:.0f} MiB (> 3x L2 in total)")
 
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    # everything device-resident runs on one side stream (CUDA graphs cannot be captured on the legacy
+    # default stream); the timing events are recorded on that same stream
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
     launchers = [abi_launcher(lib, kind, n, code, my, ins, out, stream, ALGOS[args.method]) for ins, out in sets]
 
     def step(i):
@@ -497,17 +505,38 @@ def run_workload(args, rank, local_rank, world, dist):
     seq = [launchers[(args.warmup + i) % nsets] for i in range(args.steps)]
     sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
     rc_any = 0
-    with clocks:
-        ev0.record()
-        for f in seq:
-            rc_any |= f()
-        ev1.record()
+    if args.launch == "graph":
+        # the K steps (K calls of the C ABI, one per operand set in rotation) are captured ONCE; the
+        # timed region replays them.  Programmatic (PDL) edges between the launches survive capture.
+        graph = torch.cuda.CUDAGraph()
+        launches0 = _lib.launch_count()
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+            for f in seq:
+                rc_any |= f()
+        launches = _lib.launch_count() - launches0      # kernel nodes in the graph = launches per replay
+        if rc_any:
+            _lib.check(rc_any, "bench step (capture)")
+        graph.replay()                                  # untimed: first replay uploads the executable graph
         sync()
-    if rc_any:
-        _lib.check(rc_any, "bench step")
-    launches = _lib.launch_count() - launches0
+        with clocks:
+            ev0.record()
+            graph.replay()
+            ev1.record()
+            sync()
+        timing["launch"] = "cuda graph: %d steps captured through the C ABI, one replay timed" % args.steps
+    else:
+        launches0 = _lib.launch_count()
+        with clocks:
+            ev0.record()
+            for f in seq:
+                rc_any |= f()
+            ev1.record()
+            sync()
+        if rc_any:
+            _lib.check(rc_any, "bench step")
+        launches = _lib.launch_count() - launches0
+        timing["launch"] = "eager: %d ctypes calls of the C ABI" % args.steps
     elapsed_ms = ev0.elapsed_time(ev1)
     if dist is not None:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -593,6 +622,7 @@ def run_workload(args, rank, local_rank, world, dist):
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
     del sets, launchers
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
     torch.cuda.empty_cache()
 
 
