@@ -506,18 +506,25 @@ def run_workload(args, rank, local_rank, world, dist):
     sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rc_any = 0
+    graph = None
     if args.launch == "graph":
         # the K steps (K calls of the C ABI, one per operand set in rotation) are captured ONCE; the
         # timed region replays them.  Programmatic (PDL) edges between the launches survive capture.
-        graph = torch.cuda.CUDAGraph()
-        launches0 = _lib.launch_count()
-        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
-            for f in seq:
-                rc_any |= f()
-        launches = _lib.launch_count() - launches0      # kernel nodes in the graph = launches per replay
+        try:
+            graph = torch.cuda.CUDAGraph()
+            launches0 = _lib.launch_count()
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                for f in seq:
+                    rc_any |= f()
+            launches = _lib.launch_count() - launches0  # kernel nodes in the graph = launches per replay
+            graph.replay()                              # untimed: the first replay uploads the executable graph
+        except Exception as exc:                        # e.g. another thread of the process broke the capture
+            print("bench.py: CUDA graph capture failed (%s); timing eager launches instead" % exc, file=sys.stderr)
+            graph, rc_any = None, 0
+            torch.cuda.synchronize(dev)
+    if graph is not None:
         if rc_any:
             _lib.check(rc_any, "bench step (capture)")
-        graph.replay()                                  # untimed: first replay uploads the executable graph
         sync()
         with clocks:
             ev0.record()
@@ -526,6 +533,8 @@ def run_workload(args, rank, local_rank, world, dist):
             sync()
         timing["launch"] = "cuda graph: %d steps captured through the C ABI, one replay timed" % args.steps
     else:
+        if args.launch == "graph":
+            sync()          # a rank whose capture failed keeps the barrier count of the ranks that replay
         launches0 = _lib.launch_count()
         with clocks:
             ev0.record()

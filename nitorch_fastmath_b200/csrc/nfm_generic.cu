@@ -36,115 +36,211 @@ __global__ void __launch_bounds__(128) matvec_rt_kernel(const T* __restrict__ ma
 // rows in piv[]; a column replays the exchanges with predicated swaps (skipped by a
 // warp vote when no matrix of the warp pivoted in that step).
 // ---------------------------------------------------------------------------
+// factorisation of one matrix held in registers: LU with partial pivoting (multipliers in the
+// strict lower triangle, reciprocal pivots on the diagonal, pivot rows in piv[]) or LDL^T
+// (L in the strict lower triangle, 1 / d on the diagonal)
+template <typename T, int N, bool CHOL>
+__device__ __forceinline__ void factor_in_registers(T (&a)[N][N], int (&piv)[N]) {
+  if constexpr (!CHOL) {
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K;
+      T best = tabs(a[k][k]);
+      int p = k;
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
+        const T c = tabs(a[i][k]);
+        if (c > best) {
+          best = c;
+          p = i;
+        }
+      });
+      piv[k] = p;
+      if (warp_any(p != k)) {
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const bool sw = (p == i);
+          static_for<0, N>([&](auto J) {
+            constexpr int j = J;
+            const T lo = a[k][j], hi = a[i][j];
+            a[k][j] = sw ? hi : lo;
+            a[i][j] = sw ? lo : hi;
+          });
+        });
+      }
+      const T rp = T(1) / a[k][k];
+      a[k][k] = rp;  // the reciprocal pivot is what the substitutions need
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
+        const T f = a[i][k] * rp;
+        a[i][k] = f;
+        static_for<k + 1, N>([&](auto J) {
+          constexpr int j = J;
+          a[i][j] -= f * a[k][j];
+        });
+      });
+    });
+  } else {
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K;
+      const T rp = T(1) / a[k][k];
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
+        static_for<k + 1, i + 1>([&](auto J) {
+          constexpr int j = J;
+          a[i][j] -= a[i][k] * a[j][k] * rp;
+        });
+      });
+      static_for<k + 1, N>([&](auto I) { a[I][k] *= rp; });
+      a[k][k] = rp;
+      piv[k] = k;
+    });
+  }
+}
+
+// one right-hand side against the factors above, in place
+template <typename T, int N, bool CHOL>
+__device__ __forceinline__ void substitute_in_registers(const T (&a)[N][N], const int (&piv)[N], T (&x)[N]) {
+  if constexpr (!CHOL) {
+    // the factorisation exchanged whole rows (multipliers included, as LAPACK's getrf), so
+    // all exchanges are applied to the right-hand side first, then L y = P b
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K;
+      if (warp_any(piv[k] != k)) {
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const bool sw = (piv[k] == i);
+          const T lo = x[k], hi = x[i];
+          x[k] = sw ? hi : lo;
+          x[i] = sw ? lo : hi;
+        });
+      }
+    });
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K;
+      static_for<k + 1, N>([&](auto I) { x[I] -= a[I][k] * x[k]; });
+    });
+    static_for_down<0, N>([&](auto K) {  // U x = y
+      constexpr int k = K;
+      T sum = x[k];
+      static_for<k + 1, N>([&](auto J) { sum -= a[k][J] * x[J]; });
+      x[k] = sum * a[k][k];
+    });
+  } else {
+    static_for<0, N>([&](auto K) { static_for<K + 1, N>([&](auto I) { x[I] -= a[I][K] * x[K]; }); });
+    static_for<0, N>([&](auto K) { x[K] *= a[K][K]; });
+    static_for_down<0, N>([&](auto K) { static_for<K + 1, N>([&](auto J) { x[K] -= a[J][K] * x[J]; }); });
+  }
+}
+
+// the matrix of one system out of its row-major record (transposed for right division;
+// the lower triangle mirrored for the symmetric LDL^T path)
+template <typename T, int N, bool CHOL>
+__device__ __forceinline__ void load_system(const T* src, int right, T (&a)[N][N]) {
+  static_for<0, N>([&](auto I) {
+    static_for<0, N>([&](auto J) {
+      constexpr int i = I, j = J;
+      if constexpr (CHOL) a[i][j] = src[(i > j ? i : j) * N + (i > j ? j : i)];  // lower triangle, symmetric
+      else a[i][j] = right ? src[j * N + i] : src[i * N + j];
+    });
+  });
+}
+
 template <typename T, int N, bool CHOL>
 __global__ void __launch_bounds__(128) solve_many_kernel(const T* mat, i64 as, const T* rhs, i64 bs, T* out, i64 os, int nrhs,
                                                          int right, i64 batch) {
   for (i64 b0 = i64(blockIdx.x) * blockDim.x; b0 < batch; b0 += i64(gridDim.x) * blockDim.x) {
     const bool valid = b0 + threadIdx.x < batch;
     const i64 b = valid ? b0 + threadIdx.x : batch - 1;
-    const T* src = mat + b * as;
     T a[N][N];
     int piv[N];
-    static_for<0, N>([&](auto I) {
-      static_for<0, N>([&](auto J) {
-        constexpr int i = I, j = J;
-        if constexpr (CHOL) a[i][j] = src[(i > j ? i : j) * N + (i > j ? j : i)];  // lower triangle, symmetric
-        else a[i][j] = right ? src[j * N + i] : src[i * N + j];
-      });
-    });
-    if constexpr (!CHOL) {
-      static_for<0, N>([&](auto K) {
-        constexpr int k = K;
-        T best = tabs(a[k][k]);
-        int p = k;
-        static_for<k + 1, N>([&](auto I) {
-          constexpr int i = I;
-          const T c = tabs(a[i][k]);
-          if (c > best) {
-            best = c;
-            p = i;
-          }
-        });
-        piv[k] = p;
-        if (warp_any(p != k)) {
-          static_for<k + 1, N>([&](auto I) {
-            constexpr int i = I;
-            const bool sw = (p == i);
-            static_for<0, N>([&](auto J) {
-              constexpr int j = J;
-              const T lo = a[k][j], hi = a[i][j];
-              a[k][j] = sw ? hi : lo;
-              a[i][j] = sw ? lo : hi;
-            });
-          });
-        }
-        const T rp = T(1) / a[k][k];
-        a[k][k] = rp;  // the reciprocal pivot is what the substitutions need
-        static_for<k + 1, N>([&](auto I) {
-          constexpr int i = I;
-          const T f = a[i][k] * rp;
-          a[i][k] = f;
-          static_for<k + 1, N>([&](auto J) {
-            constexpr int j = J;
-            a[i][j] -= f * a[k][j];
-          });
-        });
-      });
-    } else {
-      // LDL^T: strictly-lower part holds L, diagonal holds 1 / d
-      static_for<0, N>([&](auto K) {
-        constexpr int k = K;
-        const T rp = T(1) / a[k][k];
-        static_for<k + 1, N>([&](auto I) {
-          constexpr int i = I;
-          static_for<k + 1, i + 1>([&](auto J) {
-            constexpr int j = J;
-            a[i][j] -= a[i][k] * a[j][k] * rp;
-          });
-        });
-        static_for<k + 1, N>([&](auto I) { a[I][k] *= rp; });
-        a[k][k] = rp;
-        piv[k] = k;
-      });
-    }
+    load_system<T, N, CHOL>(mat + b * as, right, a);
+    factor_in_registers<T, N, CHOL>(a, piv);
     const T* bb = rhs + b * bs;
     T* xx = out + b * os;
     for (int c = 0; c < nrhs; ++c) {
       T x[N];
       static_for<0, N>([&](auto I) { x[I] = right ? bb[c * N + I] : bb[I * nrhs + c]; });
-      if constexpr (!CHOL) {
-        // the factorisation exchanged whole rows (multipliers included, as LAPACK's getrf), so
-        // all exchanges are applied to the right-hand side first, then L y = P b
-        static_for<0, N>([&](auto K) {
-          constexpr int k = K;
-          if (warp_any(piv[k] != k)) {
-            static_for<k + 1, N>([&](auto I) {
-              constexpr int i = I;
-              const bool sw = (piv[k] == i);
-              const T lo = x[k], hi = x[i];
-              x[k] = sw ? hi : lo;
-              x[i] = sw ? lo : hi;
-            });
-          }
-        });
-        static_for<0, N>([&](auto K) {
-          constexpr int k = K;
-          static_for<k + 1, N>([&](auto I) { x[I] -= a[I][k] * x[k]; });
-        });
-        static_for_down<0, N>([&](auto K) {  // U x = y
-          constexpr int k = K;
-          T sum = x[k];
-          static_for<k + 1, N>([&](auto J) { sum -= a[k][J] * x[J]; });
-          x[k] = sum * a[k][k];
-        });
-      } else {
-        static_for<0, N>([&](auto K) { static_for<K + 1, N>([&](auto I) { x[I] -= a[I][K] * x[K]; }); });
-        static_for<0, N>([&](auto K) { x[K] *= a[K][K]; });
-        static_for_down<0, N>([&](auto K) { static_for<K + 1, N>([&](auto J) { x[K] -= a[J][K] * x[J]; }); });
-      }
+      substitute_in_registers<T, N, CHOL>(a, piv, x);
       if (valid) static_for<0, N>([&](auto I) { (right ? xx[c * N + I] : xx[I * nrhs + c]) = x[I]; });
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// The same computation for DENSE, 16-byte aligned operands, staged by TMA.  A warp-tile
+// is 32 consecutive systems: its matrices and its right-hand sides are one contiguous byte
+// range each, so they move HBM -> shared memory with two 1-D bulk copies and the solutions
+// go back with one -- every HBM access a full burst, where the kernel above walks 32
+// records a warp at a stride of n*n / n*nrhs elements.  Every warp owns a private double
+// buffer (no CTA-wide barrier anywhere): while it factorises tile i out of one buffer,
+// tile i+1 is in flight into the other.  The solutions overwrite the right-hand sides in
+// the buffer (column c of X takes the place of column c of B), which is what the bulk
+// store sends back.  One persistent CTA of `nwarps` warps per SM.
+// ---------------------------------------------------------------------------
+constexpr int kManyMaxW = 8;
+
+template <typename T, int N, bool CHOL>
+__global__ void __launch_bounds__(kManyMaxW * 32, 1)
+    solve_many_staged_kernel(const T* __restrict__ mat, const T* __restrict__ rhs, T* __restrict__ out, const int nrhs,
+                             const int right, const i64 ntiles, const int buf_bytes) {
+  constexpr int es = int(sizeof(T));
+  constexpr uint32_t a_bytes = 32u * N * N * es;
+  const uint32_t b_bytes = 32u * N * uint32_t(nrhs) * es;
+  const int brec = N * nrhs;  // elements per right-hand-side record
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  unsigned char* const mine = smem + size_t(warp) * 2 * buf_bytes;
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + size_t(nwarps) * 2 * buf_bytes) + 2 * warp;
+
+  if (lane == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  grid_dependency_wait();
+  grid_launch_dependents();
+
+  // warp-tiles of this warp: first, first + stride, ...
+  const i64 stride = i64(gridDim.x) * nwarps;
+  const i64 first = i64(warp) * gridDim.x + blockIdx.x;
+  auto issue = [&](int b, i64 tile) {  // lane 0 only
+    unsigned char* dst = mine + b * buf_bytes;
+    mbar_arrive_expect_tx(&full[b], a_bytes + b_bytes);
+    bulk_g2s<false>(dst, mat + tile * (32 * N * N), a_bytes, &full[b], 0);
+    bulk_g2s<false>(dst + a_bytes, rhs + tile * 32 * brec, b_bytes, &full[b], 0);
+  };
+  if (lane == 0 && first < ntiles) issue(0, first);
+
+  int it = 0;
+  for (i64 tile = first; tile < ntiles; tile += stride, ++it) {
+    const int cur = it & 1;
+    if (lane == 0) {
+      bulk_wait_read<0>();  // the store of the previous tile has read the other buffer
+      if (tile + stride < ntiles) issue(cur ^ 1, tile + stride);
+    }
+    mbar_wait(&full[cur], uint32_t(it >> 1) & 1u);
+    unsigned char* buf = mine + cur * buf_bytes;
+    T a[N][N];
+    int piv[N];
+    load_system<T, N, CHOL>(reinterpret_cast<const T*>(buf) + lane * (N * N), right, a);
+    factor_in_registers<T, N, CHOL>(a, piv);
+    T* bb = reinterpret_cast<T*>(buf + a_bytes) + lane * brec;
+    for (int c = 0; c < nrhs; ++c) {
+      T x[N];
+      static_for<0, N>([&](auto I) { x[I] = right ? bb[c * N + I] : bb[I * nrhs + c]; });
+      substitute_in_registers<T, N, CHOL>(a, piv, x);
+      static_for<0, N>([&](auto I) { (right ? bb[c * N + I] : bb[I * nrhs + c]) = x[I]; });
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(out + tile * 32 * brec, buf + a_bytes, b_bytes);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();  // writes complete with the grid; shared memory must outlive the reads
 }
 
 // J^T H J (mode 0) or J H J^T (mode 1, k == d) for any 1 <= k, d <= 10:
