@@ -559,7 +559,7 @@ def run_workload(args, rank, local_rank, world, dist):
     local_ms = ev0.elapsed_time(ev1) / args.steps
     achieved = my * alg / (local_ms * 1e-3) / 1e9
     path = int(lib.nfm_last_path_was_tma())
-    kernel = {1: "nfm::tile_kernel", 2: "nfm::warp_solve_kernel", 3: "nfm::pool_kernel", 0: "nfm::strided_kernel"}[path]
+    kernel = {1: "nfm::tile_kernel", 2: "nfm::warp_solve_kernel", 3: "nfm::pool_kernel", 4: "nfm::solve_many_staged_kernel", 0: "nfm::strided_kernel"}[path]
     # dram bytes per launch come from a committed ncu capture of the default single-GPU run of this
     # workload (profiles/traffic.json): a lookup, not a measurement of this run -- null otherwise
     default_run = world == 1 and args.method == "auto" and batch == WORKLOADS[args.workload]["batch"] and not (args.kind or args.n or args.dtype)

@@ -73,6 +73,8 @@ uint64_t nfm_launch_count(void);
 /* 1 if the last call on this thread used the TMA-staged thread-per-matrix fast
  * path for its bulk (tile kernel), 2 if it used the sub-warp cooperative kernel,
  * 3 if it used the TMA-staged warp-pool kernel (pivoted ops on large records),
+ * 4 if it used the TMA-staged kernel for many right-hand sides / right division
+ * (nfm_batch_solve with nrhs > 4, nfm_batch_rsolve; dense 16-byte aligned operands),
  * 0 otherwise (strided kernel) */
 int nfm_last_path_was_tma(void);
 

@@ -4,6 +4,8 @@
 // division (sugar.lmdiv / rmdiv, sugar.py:75-191; factorisation in registers, run-time
 // loop over the right-hand sides), and J^T H J beyond the templated shapes.  Correct for
 // any batch stride; not on the measured hot path.
+#include <cstdlib>
+
 #include "nfm_pipeline.cuh"
 #include "nfm_sym_math.cuh"
 
@@ -134,13 +136,13 @@ __device__ __forceinline__ void substitute_in_registers(const T (&a)[N][N], cons
 
 // the matrix of one system out of its row-major record (transposed for right division;
 // the lower triangle mirrored for the symmetric LDL^T path)
-template <typename T, int N, bool CHOL>
+template <typename T, int N, bool CHOL, int PITCH = 1>
 __device__ __forceinline__ void load_system(const T* src, int right, T (&a)[N][N]) {
   static_for<0, N>([&](auto I) {
     static_for<0, N>([&](auto J) {
       constexpr int i = I, j = J;
-      if constexpr (CHOL) a[i][j] = src[(i > j ? i : j) * N + (i > j ? j : i)];  // lower triangle, symmetric
-      else a[i][j] = right ? src[j * N + i] : src[i * N + j];
+      if constexpr (CHOL) a[i][j] = src[((i > j ? i : j) * N + (i > j ? j : i)) * PITCH];  // lower triangle, symmetric
+      else a[i][j] = right ? src[(j * N + i) * PITCH] : src[(i * N + j) * PITCH];
     });
   });
 }
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(128) solve_many_kernel(const T* mat, i64 as, c
     const i64 b = valid ? b0 + threadIdx.x : batch - 1;
     T a[N][N];
     int piv[N];
-    load_system<T, N, CHOL>(mat + b * as, right, a);
+    load_system<T, N, CHOL, 1>(mat + b * as, right, a);
     factor_in_registers<T, N, CHOL>(a, piv);
     const T* bb = rhs + b * bs;
     T* xx = out + b * os;
@@ -171,18 +173,58 @@ __global__ void __launch_bounds__(128) solve_many_kernel(const T* mat, i64 as, c
 // is 32 consecutive systems: its matrices and its right-hand sides are one contiguous byte
 // range each, so they move HBM -> shared memory with two 1-D bulk copies and the solutions
 // go back with one -- every HBM access a full burst, where the kernel above walks 32
-// records a warp at a stride of n*n / n*nrhs elements.  Every warp owns a private double
-// buffer (no CTA-wide barrier anywhere): while it factorises tile i out of one buffer,
-// tile i+1 is in flight into the other.  The solutions overwrite the right-hand sides in
-// the buffer (column c of X takes the place of column c of B), which is what the bulk
-// store sends back.  One persistent CTA of `nwarps` warps per SM.
+// records a warp at a stride of n*n / n*nrhs elements.  Every warp owns a private ring of
+// `depth` buffers (no CTA-wide barrier anywhere): while it factorises tile i out of one
+// buffer, tiles i+1 .. i+depth-1 are in flight into the others.  The solutions overwrite the
+// right-hand sides in the buffer (column c of X takes the place of column c of B), which is
+// what the bulk store sends back.  Persistent CTAs of `nwarps` warps.
+//
+// Shared-memory banks.  Lane l works on record l of the tile, i.e. at a stride of one record.
+// When the record length shares a large factor with the 32 banks (4x4 fp32: 16 words -> 16-way,
+// 6x8 fp32: 48 words -> 16-way, 8x8: 64 words -> 32-way) every access of the elimination
+// would be serialised that many times (measured: 2.0 TB/s for the 4x4 right division against
+// 5.0 TB/s for 6x6).  For the worst shapes (`transpose` != 0, chosen by the launcher) the warp first
+// re-lays the tile out element-major with a pitch of 33 records in a per-warp scratch area
+// (coalesced reads, conflict-free writes), works there conflict-free, and lays the solutions
+// back out record-major for the bulk store.
 // ---------------------------------------------------------------------------
+constexpr int kPitch = 33;
+
+// record-major tile (32 records of `len` elements) -> element-major scratch, and back
+template <typename T>
+__device__ __forceinline__ void tile_to_scratch(const T* tile, T* scratch, int len, int lane) {
+  const int q = 32 / len, r = 32 % len;  // one step of 32 elements = q records and r elements
+  int rec = lane / len, e = lane % len;
+  for (int w = lane; w < 32 * len; w += 32) {
+    scratch[e * kPitch + rec] = tile[w];
+    rec += q;
+    e += r;
+    if (e >= len) {
+      e -= len;
+      ++rec;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void scratch_to_tile(const T* scratch, T* tile, int len, int lane) {
+  const int q = 32 / len, r = 32 % len;
+  int rec = lane / len, e = lane % len;
+  for (int w = lane; w < 32 * len; w += 32) {
+    tile[w] = scratch[e * kPitch + rec];
+    rec += q;
+    e += r;
+    if (e >= len) {
+      e -= len;
+      ++rec;
+    }
+  }
+}
 constexpr int kManyMaxW = 8;
 
 template <typename T, int N, bool CHOL>
 __global__ void __launch_bounds__(kManyMaxW * 32, 1)
     solve_many_staged_kernel(const T* __restrict__ mat, const T* __restrict__ rhs, T* __restrict__ out, const int nrhs,
-                             const int right, const i64 ntiles, const int buf_bytes) {
+                             const int right, const i64 ntiles, const int buf_bytes, const int depth, const int transpose) {
   constexpr int es = int(sizeof(T));
   constexpr uint32_t a_bytes = 32u * N * N * es;
   const uint32_t b_bytes = 32u * N * uint32_t(nrhs) * es;
@@ -190,12 +232,14 @@ __global__ void __launch_bounds__(kManyMaxW * 32, 1)
 
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  unsigned char* const mine = smem + size_t(warp) * 2 * buf_bytes;
-  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + size_t(nwarps) * 2 * buf_bytes) + 2 * warp;
+  unsigned char* const mine = smem + size_t(warp) * depth * buf_bytes;
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem + size_t(nwarps) * depth * buf_bytes) + depth * warp;
+  // element-major scratch of this warp (only when `transpose`): max(N*N, N*nrhs) x kPitch elements
+  const int slen = N * (nrhs > N ? nrhs : N);
+  T* const scratch = reinterpret_cast<T*>(smem + size_t(nwarps) * depth * (buf_bytes + 8) + 16) + size_t(warp) * slen * kPitch;
 
   if (lane == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int b = 0; b < depth; ++b) mbar_init(&full[b], 1);
     fence_mbar_init();
   }
   __syncwarp();
@@ -211,33 +255,60 @@ __global__ void __launch_bounds__(kManyMaxW * 32, 1)
     bulk_g2s<false>(dst, mat + tile * (32 * N * N), a_bytes, &full[b], 0);
     bulk_g2s<false>(dst + a_bytes, rhs + tile * 32 * brec, b_bytes, &full[b], 0);
   };
-  if (lane == 0 && first < ntiles) issue(0, first);
+  if (lane == 0)
+    for (int b = 0; b < depth - 1; ++b)
+      if (first + b * stride < ntiles) issue(b, first + b * stride);
 
-  int it = 0;
-  for (i64 tile = first; tile < ntiles; tile += stride, ++it) {
-    const int cur = it & 1;
+  int cur = 0;          // tile counter of this warp modulo depth
+  uint32_t parity = 0;  // (tile counter / depth) & 1
+  for (i64 tile = first; tile < ntiles; tile += stride) {
     if (lane == 0) {
-      bulk_wait_read<0>();  // the store of the previous tile has read the other buffer
-      if (tile + stride < ntiles) issue(cur ^ 1, tile + stride);
+      // the tile depth - 1 ahead goes into the buffer the previous tile has just left: its store must have read it
+      bulk_wait_read<0>();
+      const i64 nxt = tile + (depth - 1) * stride;
+      if (nxt < ntiles) issue(cur == 0 ? depth - 1 : cur - 1, nxt);
     }
-    mbar_wait(&full[cur], uint32_t(it >> 1) & 1u);
+    mbar_wait(&full[cur], parity);
     unsigned char* buf = mine + cur * buf_bytes;
     T a[N][N];
     int piv[N];
-    load_system<T, N, CHOL>(reinterpret_cast<const T*>(buf) + lane * (N * N), right, a);
-    factor_in_registers<T, N, CHOL>(a, piv);
-    T* bb = reinterpret_cast<T*>(buf + a_bytes) + lane * brec;
-    for (int c = 0; c < nrhs; ++c) {
-      T x[N];
-      static_for<0, N>([&](auto I) { x[I] = right ? bb[c * N + I] : bb[I * nrhs + c]; });
-      substitute_in_registers<T, N, CHOL>(a, piv, x);
-      static_for<0, N>([&](auto I) { (right ? bb[c * N + I] : bb[I * nrhs + c]) = x[I]; });
+    if (!transpose) {
+      load_system<T, N, CHOL, 1>(reinterpret_cast<const T*>(buf) + lane * (N * N), right, a);
+      factor_in_registers<T, N, CHOL>(a, piv);
+      T* bb = reinterpret_cast<T*>(buf + a_bytes) + lane * brec;
+      for (int c = 0; c < nrhs; ++c) {
+        T x[N];
+        static_for<0, N>([&](auto I) { x[I] = right ? bb[c * N + I] : bb[I * nrhs + c]; });
+        substitute_in_registers<T, N, CHOL>(a, piv, x);
+        static_for<0, N>([&](auto I) { (right ? bb[c * N + I] : bb[I * nrhs + c]) = x[I]; });
+      }
+    } else {
+      tile_to_scratch(reinterpret_cast<const T*>(buf), scratch, N * N, lane);
+      __syncwarp();
+      load_system<T, N, CHOL, kPitch>(scratch + lane, right, a);
+      __syncwarp();  // every lane holds its matrix: the scratch takes the right-hand sides
+      tile_to_scratch(reinterpret_cast<const T*>(buf + a_bytes), scratch, brec, lane);
+      factor_in_registers<T, N, CHOL>(a, piv);
+      __syncwarp();
+      T* bb = scratch + lane;
+      for (int c = 0; c < nrhs; ++c) {
+        T x[N];
+        static_for<0, N>([&](auto I) { x[I] = right ? bb[(c * N + I) * kPitch] : bb[(I * nrhs + c) * kPitch]; });
+        substitute_in_registers<T, N, CHOL>(a, piv, x);
+        static_for<0, N>([&](auto I) { (right ? bb[(c * N + I) * kPitch] : bb[(I * nrhs + c) * kPitch]) = x[I]; });
+      }
+      __syncwarp();
+      scratch_to_tile(scratch, reinterpret_cast<T*>(buf + a_bytes), brec, lane);
     }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
       bulk_s2g(out + tile * 32 * brec, buf + a_bytes, b_bytes);
       bulk_commit();
+    }
+    if (++cur == depth) {
+      cur = 0;
+      parity ^= 1u;
     }
   }
   if (lane == 0) bulk_wait_read<0>();  // writes complete with the grid; shared memory must outlive the reads
@@ -306,14 +377,80 @@ int batch_matvec_rt(int m, int n, i64 batch, const void* mat, i64 ms, const void
   return int(cudaGetLastError());
 }
 
+bool many_staged_enabled() {  // NFM_DISABLE_MANY_STAGED=1: always the one-thread-per-system global-memory kernel
+  static const bool on = [] {
+    const char* e = getenv("NFM_DISABLE_MANY_STAGED");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
+template <typename T, int N, bool CHOL>
+static int solve_many_launch(int nrhs, int right, i64 batch, const T* a, i64 as, const T* b, i64 bs, T* out, i64 os, cudaStream_t s) {
+  t_last_path_tma = 0;
+  constexpr int es = int(sizeof(T));
+  const i64 brec = i64(N) * nrhs;
+  const bool dense = as == N * N && bs == brec && os == brec && aligned16(a) && aligned16(b) && aligned16(out);
+  i64 done = 0;
+  if (dense && batch >= 64 && many_staged_enabled()) {
+    // a warp's buffer: 32 matrices + 32 right-hand-side records; 2..4 buffers per warp, up to 8 warps
+    // per CTA and as many CTAs per SM as registers and shared memory allow
+    const int buf_bytes = int((32 * (N * N + brec) * es + 127) / 128 * 128);
+    // bank-conflict degree of record-strided accesses (see the kernel): re-lay the tile out when >= 16-way.
+    // Measured (profiles/r2_nrhs_timing.txt): the three extra passes over shared memory pay only there --
+    // 4x4 fp64 right division 2.05 -> 4.60 TB/s (16-way), but 6x6 fp32 (4-way) 5.0 -> 2.9 TB/s.
+    auto degree = [](i64 len) {
+      const i64 words = len * es / 4;
+      int g = 1;
+      while (g < 32 && words % (2 * g) == 0) g *= 2;
+      return g / (es / 4);
+    };
+    const int transpose = (degree(N * N) >= 16 || degree(brec) >= 16) ? 1 : 0;
+    const int scratch_bytes = transpose ? int(N * (nrhs > N ? nrhs : N)) * kPitch * es : 0;
+    const DeviceInfo& dev = device_info();
+    const int avail = dev.max_smem_optin - 256;
+    int nwarps = avail / (2 * (buf_bytes + 8) + scratch_bytes);
+    if (nwarps > kManyMaxW) nwarps = kManyMaxW;
+    if (nwarps >= 3) {
+      int depth = (avail / nwarps - scratch_bytes) / (buf_bytes + 8);
+      if (depth > 4) depth = 4;
+      auto kern = solve_many_staged_kernel<T, N, CHOL>;
+      static std::atomic<int> attr_set[16];
+      const int d = current_device() & 15;
+      if (!attr_set[d].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
+        if (e != cudaSuccess) return int(e);
+        attr_set[d].store(1, std::memory_order_release);
+      }
+      const size_t smem = size_t(nwarps) * (depth * (buf_bytes + 8) + scratch_bytes) + 16;
+      int per_sm = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+      if (per_sm > 4) per_sm = 4;
+      const i64 ntiles = batch / 32;
+      i64 grid = (ntiles + nwarps - 1) / nwarps;
+      if (grid > i64(dev.sm_count) * per_sm) grid = i64(dev.sm_count) * per_sm;
+      cudaError_t e = launch_pdl(kern, unsigned(grid), unsigned(nwarps * 32), smem, s, a, b, out, nrhs, right, ntiles, buf_bytes, depth,
+                                 transpose);
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      if (e != cudaSuccess) return int(e);
+      t_last_path_tma = 4;
+      done = ntiles * 32;
+      if (done == batch) return 0;
+    }
+  }
+  // everything (strided / broadcast / unaligned operands), or the < 32 systems after the last warp-tile
+  solve_many_kernel<T, N, CHOL><<<grid_for(batch - done), 128, 0, s>>>(a + done * as, as, b + done * bs, bs, out + done * os, os, nrhs,
+                                                                        right, batch - done);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
 template <typename T, int N>
 static int solve_many_n(int n, int nrhs, int chol, int right, i64 batch, const T* a, i64 as, const T* b, i64 bs, T* out, i64 os,
                         cudaStream_t s) {
   if (n == N) {
-    if (chol) solve_many_kernel<T, N, true><<<grid_for(batch), 128, 0, s>>>(a, as, b, bs, out, os, nrhs, right, batch);
-    else solve_many_kernel<T, N, false><<<grid_for(batch), 128, 0, s>>>(a, as, b, bs, out, os, nrhs, right, batch);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return int(cudaGetLastError());
+    return chol ? solve_many_launch<T, N, true>(nrhs, right, batch, a, as, b, bs, out, os, s)
+                : solve_many_launch<T, N, false>(nrhs, right, batch, a, as, b, bs, out, os, s);
   }
   if constexpr (N < NFM_MAX_N) return solve_many_n<T, N + 1>(n, nrhs, chol, right, batch, a, as, b, bs, out, os, s);
   else return NFM_E_UNSUPPORTED;

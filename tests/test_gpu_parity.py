@@ -1047,9 +1047,33 @@ def test_many_right_hand_sides_and_right_division(nfm, dtype, n):
     batch = 5003
     a = _row_permuted(G.dense_shifted(batch, n, dtype, seed=n), seed=n)          # half of the lanes pivot
     spd = G.dense_spd(batch, n, dtype, seed=n + 1)
+    from nitorch_fastmath_b200 import _lib
+    lib = _lib.load()
+    esize = 4 if dtype == torch.float32 else 8
+
+    def staged(k):      # three warps' double buffers (+ transposition scratch) fit the 227 KB of shared memory
+        def degree(length):
+            words, g = length * esize // 4, 1
+            while g < 32 and words % (2 * g) == 0:
+                g *= 2
+            return g // (esize // 4)
+        buf = (32 * (n * n + n * k) * esize + 127) // 128 * 128
+        scratch = n * max(n, k) * 33 * esize if max(degree(n * n), degree(n * k)) >= 16 else 0
+        return (232448 - 256) // (2 * (buf + 8) + scratch) >= 3
+
     for k in (5, 7, 12):
         b = G.vectors((batch, n), k, dtype, seed=k)
         close(nfm.lmdiv(a.to(DEV), b.to(DEV)), P.lmdiv(a, b), dtype, 2, scale=4)
+        # dense aligned operands take the TMA-staged kernel whenever three warps' double buffers fit
+        assert lib.nfm_last_path_was_tma() == (4 if staged(k) else 0)
+        # ... which computes what the one-thread-per-system kernel computes, bit for bit (a view that is
+        # not 16-byte aligned takes that kernel)
+        if n > 1:
+            pad_a = torch.empty(batch * n * n + 1, device=DEV, dtype=dtype)[1:].view(batch, n, n).copy_(a)
+            assert pad_a.data_ptr() % 16 != 0
+            ref = nfm.lmdiv(pad_a, b.to(DEV))
+            assert lib.nfm_last_path_was_tma() == 0
+            assert torch.equal(ref, nfm.lmdiv(a.to(DEV), b.to(DEV)))
         close(nfm.lmdiv(spd.to(DEV), b.to(DEV), "chol"), P.lmdiv(spd, b, "chol"), dtype, 2, scale=4)
     for k in (1, 3, 4, 9):
         r = G.vectors((batch, k), n, dtype, seed=20 + k)                          # (batch, k, n)
