@@ -40,6 +40,9 @@ struct KParams {
   double scal1;  //  damping and step length of the fused solve + update)
 };
 
+// KParams::flags of BatchSolveKOp: X = B A^-1 with B, X  K x N row-major (one system A^T x = b per row)
+constexpr int kFlagRightDivision = 2;
+
 // ---------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------

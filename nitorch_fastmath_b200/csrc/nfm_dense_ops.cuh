@@ -120,7 +120,11 @@ struct BatchSolveOp {
   }
 };
 
-// X = A^-1 B with K right-hand sides; B and X are N x K row-major records
+// X = A^-1 B with K right-hand sides; B and X are N x K row-major records.
+// With kFlagRightDivision (sugar.rmdiv, K rows): X = B A^-1, B and X are K x N row-major -- the same
+// records read with the other index order (A transposed, one right-hand side per ROW of B).  The
+// flag is uniform over the launch: one branch picks between two fully static instantiations (per-element
+// selects between the two orders cost the 4x4 fp32 left division 7 %).
 template <typename T, int N, int K, int ALGO>
 struct BatchSolveKOp {
   using scalar = T;
@@ -131,37 +135,46 @@ struct BatchSolveKOp {
   static constexpr int kOut = N * K;
   static constexpr bool kHeavy = ALGO != NFM_ALGO_LDL && N >= 2;
 
-  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&b)[kLen1], const T (&)[1], int present,
+  __device__ static __forceinline__ void apply(const T (&a)[kLen0], const T (&b)[kLen1], const T (&z)[1], int present,
                                                int flags, T (&x)[kOut]) {
+    if (flags & kFlagRightDivision) apply_order<true>(a, b, x);
+    else apply_order<false>(a, b, x);
+  }
+
+  template <bool right>
+  __device__ static __forceinline__ void apply_order(const T (&a)[kLen0], const T (&b)[kLen1], T (&x)[kOut]) {
+    T sol[N][K];  // sol[i][c]: component i of the solution for right-hand side c
     if constexpr (ALGO == NFM_ALGO_LDL) {
       LDL<T, N> f;
-      ldl_from_dense_lower<T, N>(a, f);
+      ldl_from_dense_lower<T, N>(a, f);  // symmetric: the same factors serve both divisions
       f.factor();
 #pragma unroll
       for (int c = 0; c < K; ++c) {
-        T col[N], sol[N];
+        T col[N], s[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) col[i] = b[i * K + c];
-        f.solve(col, sol);
+        for (int i = 0; i < N; ++i) col[i] = right ? b[c * N + i] : b[i * K + c];
+        f.solve(col, s);
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[i * K + c] = sol[i];
+        for (int i = 0; i < N; ++i) sol[i][c] = s[i];
       }
     } else {
       GaussPP<T, N, K> g;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) g.a[i][j] = a[i * N + j];
+        for (int j = 0; j < N; ++j) g.a[i][j] = right ? a[j * N + i] : a[i * N + j];
 #pragma unroll
-        for (int c = 0; c < K; ++c) g.b[i][c] = b[i * K + c];
+        for (int c = 0; c < K; ++c) g.b[i][c] = right ? b[c * N + i] : b[i * K + c];
       }
       g.eliminate();
       g.back_substitute();
 #pragma unroll
       for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int c = 0; c < K; ++c) x[i * K + c] = g.b[i][c];
+        for (int c = 0; c < K; ++c) sol[i][c] = g.b[i][c];
     }
+#pragma unroll
+    for (int q = 0; q < N * K; ++q) x[q] = right ? sol[q % N][q / N] : sol[q / K][q % K];
   }
 };
 

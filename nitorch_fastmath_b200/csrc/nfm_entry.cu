@@ -303,6 +303,18 @@ int nfm_batch_rsolve(int dtype, int n, int nrows, int algo, int64_t batch, const
   if (mat == nullptr || b == nullptr || out == nullptr) return fail(NFM_E_BADARG, "NULL operand");
   if (a_stride < 0 || b_stride < 0 || out_stride < 0) return fail(NFM_E_BADARG, "negative batch stride");
   auto s = static_cast<cudaStream_t>(stream);
+  if (nrows >= 2 && nrows <= 4) {  // the register kernels of nfm_batch_solve, records read in the other index order
+    Args a;
+    a.in(0, mat, a_stride, true);
+    a.in(1, b, b_stride, true);
+    a.out(out, out_stride);
+    if (a.rc) return a.rc;
+    a.p.batch = batch;
+    a.p.flags = kFlagRightDivision;
+    if (algo == NFM_ALGO_LDL)
+      return finish(dtype == NFM_F32 ? batch_solvek_ldl_impl<float>(n, nrows, a.p, s) : batch_solvek_ldl_impl<double>(n, nrows, a.p, s));
+    return finish(dtype == NFM_F32 ? batch_solvek_lu_impl<float>(n, nrows, a.p, s) : batch_solvek_lu_impl<double>(n, nrows, a.p, s));
+  }
   const int chol = algo == NFM_ALGO_LDL;
   rc = dtype == NFM_F32 ? batch_solve_many<float>(n, nrows, chol, 1, batch, mat, a_stride, b, b_stride, out, out_stride, s)
                         : batch_solve_many<double>(n, nrows, chol, 1, batch, mat, a_stride, b, b_stride, out, out_stride, s);

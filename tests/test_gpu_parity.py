@@ -1079,6 +1079,9 @@ def test_many_right_hand_sides_and_right_division(nfm, dtype, n):
         r = G.vectors((batch, k), n, dtype, seed=20 + k)                          # (batch, k, n)
         want = (r.double() @ torch.linalg.inv(a.double())).to(dtype)              # the documented a @ inv(b)
         got = nfm.rmdiv(r.to(DEV), a.to(DEV))
+        # 2..4 rows: the register kernels of lmdiv on the TMA tile / pool path, records read in the other
+        # index order; 1 row and more than 4: the staged many-right-hand-sides kernel
+        assert lib.nfm_last_path_was_tma() == ((3 if n >= 8 or (n >= 6 and esize == 8) else 1) if 2 <= k <= 4 else 4 if staged(k) else 0)
         close(got, want, dtype, 2, scale=4)
         want_c = (r.double() @ torch.linalg.inv(spd.double())).to(dtype)
         close(nfm.rmdiv(r.to(DEV), spd.to(DEV), "chol"), want_c, dtype, 2, scale=4)
