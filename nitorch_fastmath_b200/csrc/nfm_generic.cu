@@ -183,10 +183,13 @@ __global__ void __launch_bounds__(128) solve_many_kernel(const T* mat, i64 as, c
 // When the record length shares a large factor with the 32 banks (4x4 fp32: 16 words -> 16-way,
 // 6x8 fp32: 48 words -> 16-way, 8x8: 64 words -> 32-way) every access of the elimination
 // would be serialised that many times (measured: 2.0 TB/s for the 4x4 right division against
-// 5.0 TB/s for 6x6).  For the worst shapes (`transpose` != 0, chosen by the launcher) the warp first
-// re-lays the tile out element-major with a pitch of 33 records in a per-warp scratch area
-// (coalesced reads, conflict-free writes), works there conflict-free, and lays the solutions
-// back out record-major for the bulk store.
+// 5.0 TB/s for 6x6).  Two remedies, chosen by the launcher:
+//  * right-hand sides: lanes whose records start in the same bank walk the columns in a different
+//    (rotated) order -- no extra work, most conflicts gone;
+//  * matrices (read once per system), and right-hand sides with too few columns to rotate over
+//    (`transpose` bits 0 / 1): the warp re-lays the tile out element-major with a pitch of 33 records
+//    in a per-warp scratch area (coalesced reads, conflict-free writes), works there conflict-free,
+//    and lays the solutions back out record-major for the bulk store.
 // ---------------------------------------------------------------------------
 constexpr int kPitch = 33;
 
@@ -224,7 +227,8 @@ constexpr int kManyMaxW = 8;
 template <typename T, int N, bool CHOL>
 __global__ void __launch_bounds__(kManyMaxW * 32, 1)
     solve_many_staged_kernel(const T* __restrict__ mat, const T* __restrict__ rhs, T* __restrict__ out, const int nrhs,
-                             const int right, const i64 ntiles, const int buf_bytes, const int depth, const int transpose) {
+                             const int right, const i64 ntiles, const int buf_bytes, const int depth, const int transpose,
+                             const int rot_shift) {
   constexpr int es = int(sizeof(T));
   constexpr uint32_t a_bytes = 32u * N * N * es;
   const uint32_t b_bytes = 32u * N * uint32_t(nrhs) * es;
@@ -234,8 +238,9 @@ __global__ void __launch_bounds__(kManyMaxW * 32, 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   unsigned char* const mine = smem + size_t(warp) * depth * buf_bytes;
   uint64_t* const full = reinterpret_cast<uint64_t*>(smem + size_t(nwarps) * depth * buf_bytes) + depth * warp;
-  // element-major scratch of this warp (only when `transpose`): max(N*N, N*nrhs) x kPitch elements
-  const int slen = N * (nrhs > N ? nrhs : N);
+  // element-major scratch of this warp (`transpose` bit 0: matrices, bit 1: right-hand sides): the longer
+  // of the two record lengths that go through it, x kPitch elements
+  const int slen = ((transpose & 2) && nrhs > N) || !(transpose & 1) ? N * nrhs : N * N;
   T* const scratch = reinterpret_cast<T*>(smem + size_t(nwarps) * depth * (buf_bytes + 8) + 16) + size_t(warp) * slen * kPitch;
 
   if (lane == 0) {
@@ -272,23 +277,29 @@ __global__ void __launch_bounds__(kManyMaxW * 32, 1)
     unsigned char* buf = mine + cur * buf_bytes;
     T a[N][N];
     int piv[N];
-    if (!transpose) {
+    if (transpose & 1) {  // matrices through the element-major scratch
+      tile_to_scratch(reinterpret_cast<const T*>(buf), scratch, N * N, lane);
+      __syncwarp();
+      load_system<T, N, CHOL, kPitch>(scratch + lane, right, a);
+      __syncwarp();  // every lane holds its matrix: the scratch may take the right-hand sides
+    } else {
       load_system<T, N, CHOL, 1>(reinterpret_cast<const T*>(buf) + lane * (N * N), right, a);
-      factor_in_registers<T, N, CHOL>(a, piv);
+    }
+    if (transpose & 2) tile_to_scratch(reinterpret_cast<const T*>(buf + a_bytes), scratch, brec, lane);
+    factor_in_registers<T, N, CHOL>(a, piv);
+    if (!(transpose & 2)) {
       T* bb = reinterpret_cast<T*>(buf + a_bytes) + lane * brec;
-      for (int c = 0; c < nrhs; ++c) {
+      // lanes whose records start in the same bank (lane, lane + 32/g, ... for a g-way conflicting record
+      // length) take the right-hand sides in a different order, so that they touch different banks
+      int c = (lane >> rot_shift) % nrhs;
+      for (int done = 0; done < nrhs; ++done) {
         T x[N];
         static_for<0, N>([&](auto I) { x[I] = right ? bb[c * N + I] : bb[I * nrhs + c]; });
         substitute_in_registers<T, N, CHOL>(a, piv, x);
         static_for<0, N>([&](auto I) { (right ? bb[c * N + I] : bb[I * nrhs + c]) = x[I]; });
+        c = c + 1 == nrhs ? 0 : c + 1;
       }
     } else {
-      tile_to_scratch(reinterpret_cast<const T*>(buf), scratch, N * N, lane);
-      __syncwarp();
-      load_system<T, N, CHOL, kPitch>(scratch + lane, right, a);
-      __syncwarp();  // every lane holds its matrix: the scratch takes the right-hand sides
-      tile_to_scratch(reinterpret_cast<const T*>(buf + a_bytes), scratch, brec, lane);
-      factor_in_registers<T, N, CHOL>(a, piv);
       __syncwarp();
       T* bb = scratch + lane;
       for (int c = 0; c < nrhs; ++c) {
@@ -405,8 +416,22 @@ static int solve_many_launch(int nrhs, int right, i64 batch, const T* a, i64 as,
       while (g < 32 && words % (2 * g) == 0) g *= 2;
       return g / (es / 4);
     };
-    const int transpose = (degree(N * N) >= 16 || degree(brec) >= 16) ? 1 : 0;
-    const int scratch_bytes = transpose ? int(N * (nrhs > N ? nrhs : N)) * kPitch * es : 0;
+    static const int transpose_from = [] {  // tuning aid: NFM_MANY_TRANSPOSE_FROM=64 never re-lays a tile out
+      const char* e = getenv("NFM_MANY_TRANSPOSE_FROM");
+      return e ? atoi(e) : 16;
+    }();
+    // matrices: read once per system, so one pass through the scratch pays from 16-way conflicts (4x4, 8x8);
+    // right-hand sides: the lane-rotated column order (below) removes most conflicts without any extra pass
+    // (6x8 fp32 5.2 TB/s rotated, 2.8 through the scratch) unless there are too few columns to rotate over
+    const int transpose = (degree(N * N) >= transpose_from ? 1 : 0) | (degree(brec) >= transpose_from && nrhs < 4 ? 2 : 0);
+    // lanes l and l + 32/g start in the same bank when the right-hand-side record conflicts g-way
+    int g = 1;
+    while (g < 32 && (brec * es / 4) % (2 * g) == 0) g *= 2;
+    int rot_shift = 0;
+    while ((32 / g) >> (rot_shift + 1)) ++rot_shift;   // log2(32 / g)
+    if (g == 1) rot_shift = 5;                          // odd record length: conflict free, no rotation
+    const int slen = ((transpose & 2) && nrhs > N) || !(transpose & 1) ? N * nrhs : N * N;  // as in the kernel
+    const int scratch_bytes = transpose ? slen * kPitch * es : 0;
     const DeviceInfo& dev = device_info();
     const int avail = dev.max_smem_optin - 256;
     int nwarps = avail / (2 * (buf_bytes + 8) + scratch_bytes);
@@ -430,7 +455,7 @@ static int solve_many_launch(int nrhs, int right, i64 batch, const T* a, i64 as,
       i64 grid = (ntiles + nwarps - 1) / nwarps;
       if (grid > i64(dev.sm_count) * per_sm) grid = i64(dev.sm_count) * per_sm;
       cudaError_t e = launch_pdl(kern, unsigned(grid), unsigned(nwarps * 32), smem, s, a, b, out, nrhs, right, ntiles, buf_bytes, depth,
-                                 transpose);
+                                 transpose, rot_shift);
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       if (e != cudaSuccess) return int(e);
       t_last_path_tma = 4;

@@ -1058,7 +1058,8 @@ def test_many_right_hand_sides_and_right_division(nfm, dtype, n):
                 g *= 2
             return g // (esize // 4)
         buf = (32 * (n * n + n * k) * esize + 127) // 128 * 128
-        scratch = n * max(n, k) * 33 * esize if max(degree(n * n), degree(n * k)) >= 16 else 0
+        ta, tb = degree(n * n) >= 16, degree(n * k) >= 16 and k < 4      # matrices / right-hand sides re-laid out
+        scratch = (n * k if (tb and k > n) or not ta else n * n) * 33 * esize if ta or tb else 0
         return (232448 - 256) // (2 * (buf + 8) + scratch) >= 3
 
     for k in (5, 7, 12):
