@@ -222,10 +222,17 @@ __device__ __forceinline__ void scratch_to_tile(const T* scratch, T* tile, int l
     }
   }
 }
-constexpr int kManyMaxW = 8;
+// Warps per CTA = register budget (__launch_bounds__): the kernel is bound by the latency of its
+// dependent chains (ncu, 8 warps: issue slots 38 % busy, dominant stall `wait`), so small orders, whose
+// factors need few registers, run 12-16 warps with a shallower ring instead of 8 with a deeper one.
+template <typename T, int N>
+constexpr int many_max_warps() {
+  if (sizeof(T) == 4) return N <= 6 ? 16 : N <= 9 ? 12 : 8;
+  return N <= 4 ? 16 : N <= 6 ? 12 : 8;
+}
 
 template <typename T, int N, bool CHOL>
-__global__ void __launch_bounds__(kManyMaxW * 32, 1)
+__global__ void __launch_bounds__(many_max_warps<T, N>() * 32, 1)
     solve_many_staged_kernel(const T* __restrict__ mat, const T* __restrict__ rhs, T* __restrict__ out, const int nrhs,
                              const int right, const i64 ntiles, const int buf_bytes, const int depth, const int transpose,
                              const int rot_shift) {
@@ -435,7 +442,7 @@ static int solve_many_launch(int nrhs, int right, i64 batch, const T* a, i64 as,
     const DeviceInfo& dev = device_info();
     const int avail = dev.max_smem_optin - 256;
     int nwarps = avail / (2 * (buf_bytes + 8) + scratch_bytes);
-    if (nwarps > kManyMaxW) nwarps = kManyMaxW;
+    if (nwarps > many_max_warps<T, N>()) nwarps = many_max_warps<T, N>();
     if (nwarps >= 3) {
       int depth = (avail / nwarps - scratch_bytes) / (buf_bytes + 8);
       if (depth > 4) depth = 4;
