@@ -10,7 +10,10 @@ the default workload is BASELINE.json configs[1], the 256^3-voxel 3x3
 compact-symmetric solve in fp32 (16 777 216 matrices, 48 B each).
 
   value   whole-job matrices/s with operands resident in HBM, CUDA events on
-          the launch stream, K back-to-back launches through the C ABI.
+          the launch stream, K back-to-back launches through the C ABI.  The K
+          calls are captured once in a CUDA graph and ONE replay is timed
+          (--launch graph, the default: with 16 us launches at 8 GPUs the Python
+          loop itself was 8 % of the region); --launch eager times K ctypes calls.
   e2e     the same metric through the public API with HOST (pinned) operands:
           chunked H2D -> kernel -> D2H inside the timed region.
   N > 1   strong scaling (north star): the batch is split into N contiguous
