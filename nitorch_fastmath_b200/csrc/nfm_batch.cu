@@ -1,5 +1,7 @@
 // dense batched inverse / det / matvec / solve for one scalar type
 // (-DNFM_SCALAR) and one part (-DNFM_PART)
+#include <cstdlib>
+
 #include "nfm_dense_ops.cuh"
 #include "nfm_impl.cuh"
 #include "nfm_sym_ops.cuh"
@@ -13,8 +15,19 @@ template <typename T, int ALGO> struct SolBind { template <int N> using Op = Bat
 template <typename T, int K, int ALGO> struct SolKBind { template <int N> using Op = BatchSolveKOp<T, N, K, ALGO>; };
 
 #if NFM_PART == 0
+template <typename T> struct InvPairBind { template <int N> using Op = BatchInvPairOp<T, N>; };
+static bool pair_inverse_enabled() {  // NFM_DISABLE_PAIR_INVERSE=1: one thread per matrix for every order
+  static const bool on = [] {
+    const char* e = getenv("NFM_DISABLE_PAIR_INVERSE");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 template <typename T>
 int batch_inv_lu_impl(int n, const KParams& p, cudaStream_t s) {
+  // fp64 orders 8..10: two lanes per matrix (the one-thread form is register-bound there)
+  if constexpr (sizeof(T) == 8)
+    if (n >= 8 && pair_inverse_enabled()) return DispatchN<InvPairBind<T>::template Op, 8, NFM_MAX_N>::run(n, p, s);
   return DispatchN<InvBind<T, NFM_ALGO_AUTO>::template Op, 1, NFM_MAX_N>::run(n, p, s);
 }
 template int batch_inv_lu_impl<NFM_SCALAR>(int, const KParams&, cudaStream_t);

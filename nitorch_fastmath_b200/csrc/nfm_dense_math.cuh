@@ -140,4 +140,96 @@ struct GaussJordan {
   }
 };
 
+// The same elimination with TWO lanes per matrix (lanes 2m and 2m+1 of a warp): lane h holds the
+// columns [h*CH, h*CH + CH) of every row, CH = ceil(N / 2) -- half the registers, half the chain.
+// Columns are the natural cut: the pivot search of step k runs inside ONE lane (the owner of column
+// k, known at compile time), row exchanges and the elimination touch each lane's own columns only,
+// and what crosses lanes per step is the pivot row index, 1 / pivot and the N multipliers of column
+// k (shuffles from the owner).  The final column un-permutation costs nothing: each lane tracks
+// where its columns end up and stores them there.  Element for element the arithmetic is that of
+// GaussJordan<T, N>::invert(), so the results are bit-identical.
+template <typename T, int N>
+struct GaussJordanPair {
+  static constexpr int CH = (N + 1) / 2;
+
+  // `rec`: the row-major N x N record in shared memory (read, then overwritten with the inverse);
+  // every lane of the warp must call this (shuffles with a full mask)
+  __device__ static __forceinline__ void invert_in_place(T* rec, int lane) {
+    const int h = lane & 1, c0 = h * CH, pair0 = lane & ~1;
+    T a[N][CH];
+    static_for<0, N>([&](auto I) {
+      static_for<0, CH>([&](auto J) {
+        constexpr int i = I, jl = J;
+        a[i][jl] = (N % 2 == 0 || c0 + jl < N) ? rec[i * N + c0 + jl] : T(0);  // odd N: the last slot of lane 1 is padding
+      });
+    });
+    __syncwarp();  // both lanes of every pair hold their halves: the record may take the result
+    int piv[N];
+    static_for<0, N>([&](auto K) {
+      constexpr int k = K, owner = k / CH, kl = k % CH;
+      const int src = pair0 | owner;
+      T best = tabs(a[k][kl]);
+      int p = k;
+      static_for<k + 1, N>([&](auto I) {
+        constexpr int i = I;
+        const T c = tabs(a[i][kl]);
+        if (c > best) {
+          best = c;
+          p = i;
+        }
+      });
+      p = __shfl_sync(0xffffffffu, p, src);
+      piv[k] = p;
+      if (warp_any(p != k)) {
+        static_for<k + 1, N>([&](auto I) {
+          constexpr int i = I;
+          const bool sw = (p == i);
+          static_for<0, CH>([&](auto J) {
+            constexpr int jl = J;
+            const T lo = a[k][jl], hi = a[i][jl];
+            a[k][jl] = sw ? hi : lo;
+            a[i][jl] = sw ? lo : hi;
+          });
+        });
+      }
+      const T rp = __shfl_sync(0xffffffffu, T(1) / a[k][kl], src);
+      T f[N];
+      static_for<0, N>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (i != k) f[i] = __shfl_sync(0xffffffffu, a[i][kl], src);
+      });
+      if (h == owner) {
+        static_for<0, N>([&](auto I) { a[I][kl] = (int(I) == k) ? T(1) : T(0); });
+      }
+      static_for<0, CH>([&](auto J) { a[k][J] *= rp; });
+      static_for<0, N>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (i != k) {
+          static_for<0, CH>([&](auto J) {
+            constexpr int jl = J;
+            a[i][jl] -= f[i] * a[k][jl];
+          });
+        }
+      });
+    });
+    // (P A)^-1 = A^-1 P^T: the column exchanges k <-> piv[k], k = N-1 .. 0, applied to the POSITION
+    // of each of this lane's columns instead of to the data
+    int w[CH];
+    static_for<0, CH>([&](auto J) { w[J] = c0 + J; });
+    static_for_down<0, N>([&](auto K) {
+      constexpr int k = K;
+      const int pk = piv[k];
+      if (warp_any(pk != k)) {
+        static_for<0, CH>([&](auto J) { w[J] = w[J] == k ? pk : (w[J] == pk ? k : w[J]); });
+      }
+    });
+    static_for<0, N>([&](auto I) {
+      static_for<0, CH>([&](auto J) {
+        constexpr int i = I, jl = J;
+        if (N % 2 == 0 || c0 + jl < N) rec[i * N + w[jl]] = a[i][jl];
+      });
+    });
+  }
+};
+
 }  // namespace nfm

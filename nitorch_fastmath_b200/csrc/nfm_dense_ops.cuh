@@ -59,6 +59,18 @@ struct BatchInvOp {
   }
 };
 
+// Pivoted Gauss-Jordan inverse with two lanes per matrix on the warp-pool kernel (dense 16-byte
+// aligned batches); the strided kernel and the tail of a launch use the one-thread form it inherits.
+// For the orders whose one-thread form is register-bound: fp64 n = 8..10 (200 registers of matrix
+// per thread, 255-register kernels with spills, 8 warps per SM).
+template <typename T, int N>
+struct BatchInvPairOp : BatchInvOp<T, N, NFM_ALGO_AUTO> {
+  static constexpr int kPairLanes = 2;
+  __device__ static __forceinline__ void apply_pair(unsigned char* record, int lane, int flags) {
+    GaussJordanPair<T, N>::invert_in_place(reinterpret_cast<T*>(record), lane);
+  }
+};
+
 template <typename T, int N>
 struct BatchDetOp {
   using scalar = T;

@@ -81,6 +81,14 @@ __device__ __forceinline__ void apply_op(const KParams& p, const R0& r0, const R
   }
 }
 
+// Ops whose matrices are worked on by TWO lanes each (pool_kernel only) declare `kPairLanes = 2` and
+//     __device__ static void apply_pair(unsigned char* record, int lane, int flags);
+// which reads the staged record, computes and writes the result IN PLACE into the same bytes.
+template <class Op, class = void>
+struct pair_lanes { static constexpr int value = 1; };
+template <class Op>
+struct pair_lanes<Op, std::void_t<decltype(Op::kPairLanes)>> { static constexpr int value = Op::kPairLanes; };
+
 constexpr int kSegs = 8;     // segments per tile in the SEG layout
 constexpr int kSegPad = 16;  // bytes of skew per segment
 // The number of matrices in a tile is a run-time value (so that a launch can be
@@ -104,7 +112,8 @@ struct TileGeom {
   static constexpr int kBytes3 = bytes(len3<Op>::value);
   static constexpr int kBytesOut = bytes(Op::kOut);
   static constexpr int kFootOut = footprint(Op::kOut);
-  static_assert(kTile % kTileGran == 0, "tile capacity must be a multiple of kTileGran matrices");
+  static_assert(kTile % kTileGran == 0 || (kTile == 16 && pair_lanes<Op>::value == 2),
+                "tile capacity must be a multiple of kTileGran matrices (16-matrix warp tiles of two-lane ops excepted)");
   static_assert(!SEG || (bytes(Op::kLen0) / kSegs) % 16 == 0, "segments must keep the 16 B alignment of bulk copies");
   static_assert(kBytes0 % 16 == 0 && kBytes1 % 16 == 0 && kBytes2 % 16 == 0 && kBytesOut % 16 == 0,
                 "tile byte counts must be multiples of 16 for TMA bulk copies");
@@ -439,8 +448,8 @@ __global__ void __launch_bounds__(THREADS)
 // ---------------------------------------------------------------------------
 template <class Op, int MPT, bool SEG>
 struct PoolGeom {
-  using G = TileGeom<Op, 32, MPT, SEG>;
-  static constexpr int kWarpTile = 32 * MPT;
+  using G = TileGeom<Op, 32 / pair_lanes<Op>::value, MPT, SEG>;  // two-lane ops: 16 matrices per warp
+  static constexpr int kWarpTile = G::kTile;
   static constexpr int in_bytes(int mask) {
     return ((mask & 1) ? G::footprint(Op::kLen0) : 0) + ((mask & 2) ? G::footprint(Op::kLen1) : 0) +
            ((mask & 4) ? G::footprint(Op::kLen2) : 0);
@@ -563,28 +572,35 @@ __global__ void __launch_bounds__(MAXW * 32, 1)
       __syncwarp();
     }
 
-    T r0[MPT][Op::kLen0], r1[MPT][Op::kLen1], r2[MPT][Op::kLen2];
+    if constexpr (pair_lanes<Op>::value == 2) {
+      // two lanes per matrix (half of the columns each): the op reads its record out of the buffer,
+      // and writes the result over it, by itself
+      static_assert(MPT == 1 && Op::kOut == Op::kLen0 && Op::kUse == 1, "two-lane ops: one operand, result in place");
+      Op::apply_pair(sbuf + G::template rec_offset<Op::kLen0>(lane >> 1), lane, p.flags);
+    } else {
+      T r0[MPT][Op::kLen0], r1[MPT][Op::kLen1], r2[MPT][Op::kLen2];
 #pragma unroll
-    for (int j = 0; j < MPT; ++j) {
-      const int m = lane + j * 32;
-      if (staged & 1) load_record(reinterpret_cast<const T*>(sbuf + G::template rec_offset<Op::kLen0>(m)), r0[j]);
-      else if (p.present & 1) load_record_scalar(g0, r0[j]);
-      else zero_record(r0[j]);
-      if (staged & 2) load_record(reinterpret_cast<const T*>(sbuf + f0 + G::template rec_offset<Op::kLen1>(m)), r1[j]);
-      else if (p.present & 2) load_record_scalar(g1, r1[j]);
-      else zero_record(r1[j]);
-      if (staged & 4) load_record(reinterpret_cast<const T*>(sbuf + f0 + f1 + G::template rec_offset<Op::kLen2>(m)), r2[j]);
-      else if (p.present & 4) load_record_scalar(g2, r2[j]);
-      else zero_record(r2[j]);
-    }
-    __syncwarp();  // every lane holds its inputs: the buffer now takes the results
+      for (int j = 0; j < MPT; ++j) {
+        const int m = lane + j * 32;
+        if (staged & 1) load_record(reinterpret_cast<const T*>(sbuf + G::template rec_offset<Op::kLen0>(m)), r0[j]);
+        else if (p.present & 1) load_record_scalar(g0, r0[j]);
+        else zero_record(r0[j]);
+        if (staged & 2) load_record(reinterpret_cast<const T*>(sbuf + f0 + G::template rec_offset<Op::kLen1>(m)), r1[j]);
+        else if (p.present & 2) load_record_scalar(g1, r1[j]);
+        else zero_record(r1[j]);
+        if (staged & 4) load_record(reinterpret_cast<const T*>(sbuf + f0 + f1 + G::template rec_offset<Op::kLen2>(m)), r2[j]);
+        else if (p.present & 4) load_record_scalar(g2, r2[j]);
+        else zero_record(r2[j]);
+      }
+      __syncwarp();  // every lane holds its inputs: the buffer now takes the results
 
 #pragma unroll
-    for (int j = 0; j < MPT; ++j) {
-      T o[Op::kOut], r3[len3<Op>::value];
-      zero_record(r3);  // pool ops take at most three inputs
-      apply_op<Op>(p, r0[j], r1[j], r2[j], r3, o);
-      store_record(reinterpret_cast<T*>(sbuf + G::template rec_offset<Op::kOut>(lane + j * 32)), o);
+      for (int j = 0; j < MPT; ++j) {
+        T o[Op::kOut], r3[len3<Op>::value];
+        zero_record(r3);  // pool ops take at most three inputs
+        apply_op<Op>(p, r0[j], r1[j], r2[j], r3, o);
+        store_record(reinterpret_cast<T*>(sbuf + G::template rec_offset<Op::kOut>(lane + j * 32)), o);
+      }
     }
     if (ragged) {
       __syncwarp();
@@ -795,7 +811,8 @@ struct PoolTune {
 #else
   static constexpr bool kEnabled = Op::kHeavy && B::kInBytes >= 256;
 #endif
-  static constexpr int kMaxW = sizeof(typename Op::scalar) == 8 ? 8 : 12;
+  // (two-lane ops hold half a matrix per lane: 12 warps = 168 registers also in fp64)
+  static constexpr int kMaxW = (sizeof(typename Op::scalar) == 8 && pair_lanes<Op>::value == 1) ? 8 : 12;
   static constexpr int kMpt = 1;
   static void geometry(int buf_bytes, int max_smem, int& warps, int& nbuf) {
     int nbuf_max = (max_smem - 512) / (buf_bytes + 12);

@@ -230,6 +230,13 @@ def test_pool_kernel_tile_boundaries(nfm, batch):
         x = nfm.batchinv(a.to(DEV))
         assert _lib.load().nfm_last_path_was_tma() == 3      # TMA-staged warp-pool kernel
         close(x, P.batchinv(a), dtype, 2, scale=4)
+        if dtype == torch.float64:
+            # fp64 orders 8..10 invert with TWO lanes per matrix on the pool kernel (16-matrix warp tiles);
+            # a view 8 bytes off the 16-byte grid takes the one-thread-per-matrix strided kernel: same bits
+            off = torch.empty(batch * n * n + 1, device=DEV, dtype=dtype)[1:].view(batch, n, n).copy_(a)
+            y = nfm.batchinv(off)
+            assert _lib.load().nfm_last_path_was_tma() == 0
+            assert torch.equal(x, y)
         close(nfm.batchdet(a.to(DEV)), P.batchdet(a), dtype, 0, scale=4)
         close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), dtype, scale=4)
 
