@@ -410,9 +410,9 @@ static int solve_many_launch(int nrhs, int right, i64 batch, const T* a, i64 as,
   const i64 brec = i64(N) * nrhs;
   const bool dense = as == N * N && bs == brec && os == brec && aligned16(a) && aligned16(b) && aligned16(out);
   i64 done = 0;
-  if (dense && batch >= 64 && many_staged_enabled()) {
-    // a warp's buffer: 32 matrices + 32 right-hand-side records; 2..4 buffers per warp, up to 8 warps
-    // per CTA and as many CTAs per SM as registers and shared memory allow
+  if (dense && batch >= 64 && nrhs <= 256 && many_staged_enabled()) {  // (more columns than that never fit three warps)
+    // a warp's buffer: 32 matrices + 32 right-hand-side records; 2..4 buffers per warp, up to
+    // many_max_warps() warps per CTA and as many CTAs per SM as registers and shared memory allow
     const int buf_bytes = int((32 * (N * N + brec) * es + 127) / 128 * 128);
     // bank-conflict degree of record-strided accesses (see the kernel): re-lay the tile out when >= 16-way.
     // Measured (profiles/r2_nrhs_timing.txt): the three extra passes over shared memory pay only there --
