@@ -190,7 +190,7 @@ def _row_permuted(a, seed):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("n", [4, 5, 6, 8, 10])
+@pytest.mark.parametrize("n", [4, 5, 6, 8, 9, 10])
 def test_pivoting_differs_between_lanes_of_a_warp(nfm, dtype, n):
     """The pivoted eliminations skip the row / column exchanges of a step when no
     matrix of the warp needs them (warp vote).  Here half of the lanes need them."""
@@ -224,7 +224,7 @@ def test_pool_kernel_tile_boundaries(nfm, batch):
     tiles, buffers handed from warp to warp): batches around the warp tile and
     around one / several rounds of the pool."""
     from nitorch_fastmath_b200 import _lib
-    for n, dtype in ((8, torch.float64), (10, torch.float32), (10, torch.float64)):
+    for n, dtype in ((8, torch.float64), (9, torch.float64), (10, torch.float32), (10, torch.float64)):
         a = _row_permuted(G.dense_shifted(batch, n, dtype, seed=batch + n), seed=batch)
         b = G.vectors(batch, n, dtype, seed=batch + 1)
         x = nfm.batchinv(a.to(DEV))
@@ -232,10 +232,10 @@ def test_pool_kernel_tile_boundaries(nfm, batch):
         close(x, P.batchinv(a), dtype, 2, scale=4)
         if dtype == torch.float64:
             # fp64 orders 8..10 invert with TWO lanes per matrix on the pool kernel (16-matrix warp tiles);
-            # a view 8 bytes off the 16-byte grid takes the one-thread-per-matrix strided kernel: same bits
-            off = torch.empty(batch * n * n + 1, device=DEV, dtype=dtype)[1:].view(batch, n, n).copy_(a)
+            # records spaced wider than their length take the one-thread-per-matrix strided kernel: same bits
+            off = torch.empty(batch, n * n + 2, device=DEV, dtype=dtype)[:, :n * n].view(batch, n, n).copy_(a)
             y = nfm.batchinv(off)
-            assert _lib.load().nfm_last_path_was_tma() == 0
+            assert _lib.load().nfm_last_path_was_tma() == (0 if batch > 1 else 3)   # one record has no batch stride
             assert torch.equal(x, y)
         close(nfm.batchdet(a.to(DEV)), P.batchdet(a), dtype, 0, scale=4)
         close(nfm.solvevec(a.to(DEV), b.to(DEV)), P.solvevec(a, b), dtype, scale=4)
