@@ -74,7 +74,8 @@ uint64_t nfm_launch_count(void);
  * path for its bulk (tile kernel), 2 if it used the sub-warp cooperative kernel,
  * 3 if it used the TMA-staged warp-pool kernel (pivoted ops on large records),
  * 4 if it used the TMA-staged kernel for many right-hand sides / right division
- * (nfm_batch_solve with nrhs > 4, nfm_batch_rsolve; dense 16-byte aligned operands),
+ * (nfm_batch_solve with nrhs > 4, nfm_batch_rsolve with 1 or more than 4 rows;
+ * dense 16-byte aligned operands),
  * 0 otherwise (strided kernel) */
 int nfm_last_path_was_tma(void);
 
@@ -125,6 +126,9 @@ int nfm_batch_det(int dtype, int n, int64_t batch,
 
 /* X = A^-1 B ; A: n x n row-major, B and X: n x nrhs row-major records.
  * algo: NFM_ALGO_LU (partial pivoting) or NFM_ALGO_LDL (Cholesky; A SPD).
+ * nrhs 1..4: register kernels on the TMA tile / pool path; more: factors in
+ * registers, run-time loop over the right-hand sides out of TMA-staged warp tiles.
+ * out may alias b.
  * Replaces: sugar.lmdiv / solvevec  sugar.py:75-137, :290-341. */
 int nfm_batch_solve(int dtype, int n, int nrhs, int algo, int64_t batch,
                     const void *a, int64_t a_stride,
@@ -132,7 +136,9 @@ int nfm_batch_solve(int dtype, int n, int nrhs, int algo, int64_t batch,
                     void *out, int64_t out_stride, void *stream);
 
 /* X = B A^-1 (right division) ; A: n x n row-major, B and X: nrows x n row-major
- * records -- solved as A^T x_r = b_r for every row r, without transposed copies.
+ * records -- solved as A^T x_r = b_r for every row r, without transposed copies
+ * (2..4 rows: the register kernels of nfm_batch_solve reading the records in the
+ * other index order).  out may alias b.
  * Replaces: sugar.rmdiv  sugar.py:140-191 (documented meaning A x B^-1; as written
  * the reference returns (B^-1 A)^T). */
 int nfm_batch_rsolve(int dtype, int n, int nrows, int algo, int64_t batch,
