@@ -1095,6 +1095,14 @@ def test_many_right_hand_sides_and_right_division(nfm, dtype, n):
         close(nfm.rmdiv(r.to(DEV), spd.to(DEV), "chol"), want_c, dtype, 2, scale=4)
         out = torch.empty(batch, k, n, device=DEV, dtype=dtype)
         assert nfm.rmdiv(r.to(DEV), a.to(DEV), out=out) is out and torch.equal(out, got)
+    # the solutions may overwrite the right-hand sides (register kernels and the staged kernel alike)
+    for k in (3, 6):
+        b = G.vectors((batch, n), k, dtype, seed=90 + k).to(DEV)
+        want = nfm.lmdiv(a.to(DEV), b)
+        assert nfm.lmdiv(a.to(DEV), b, out=b) is b and torch.equal(b, want)
+        r = G.vectors((batch, k), n, dtype, seed=95 + k).to(DEV)
+        want = nfm.rmdiv(r, a.to(DEV))
+        assert nfm.rmdiv(r, a.to(DEV), out=r) is r and torch.equal(r, want)
     # broadcasting: one system for the whole batch
     r = G.vectors((batch, 2), n, dtype, seed=77)
     close(nfm.rmdiv(r.to(DEV), a[0].to(DEV)), (r.double() @ torch.linalg.inv(a[0].double())).to(dtype), dtype, 2, scale=4)
